@@ -1,0 +1,18 @@
+# Builds libtmb.so (the C-ABI product library, sm_100a only) in-tree.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
+SRCS := $(wildcard tomobar_b200/csrc/*.cu)
+OBJS := $(SRCS:.cu=.o)
+LIB := tomobar_b200/libtmb.so
+
+all: $(LIB)
+
+%.o: %.cu tomobar_b200/csrc/tmb_common.h include/tmb.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lcufft
+
+clean:
+	rm -f $(OBJS) $(LIB)

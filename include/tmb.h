@@ -1,0 +1,128 @@
+/*
+ * tmb.h -- C ABI of libtmb.so: the B200 (sm_100a) parallel-beam reconstruction hot path.
+ *
+ * This is the drop-in boundary for dkazanc/ToMoBAR's GPU hot path.  Every entry point names
+ * the reference interface it replaces (paths relative to the reference checkout).  All data
+ * pointers are DEVICE pointers unless the name ends in `_host`; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Functions return 0 on success and a
+ * negative code on failure; tmb_last_error() returns the message (thread-local).
+ *
+ * Layouts (reference conventions, C-contiguous fp32):
+ *   volume   vol [nz][n][n]      row r <-> +y, column c <-> +x   (astra_base.py:215-222)
+ *   sinogram sino[nz][na][nu]    ["detY","angles","detX"]        (astra_base.py:244-255)
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef TMB_H
+#define TMB_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMB_OK 0
+#define TMB_ERR_ARG (-1)
+#define TMB_ERR_CUDA (-2)
+#define TMB_ERR_UNSUPPORTED (-3)
+
+/* data-fidelity selector of tmb_residual (data_fidelities.py:28-39) */
+#define TMB_FID_LS 0
+#define TMB_FID_PWLS 1
+#define TMB_FID_KL 2
+
+typedef struct tmb_geom tmb_geom; /* opaque geometry + launch plan */
+
+int tmb_version(void);
+const char *tmb_last_error(void);
+
+/* ---- geometry --------------------------------------------------------------------------
+ * Replaces AstraBase._set_vol3d_geometry / _set_gpu_projection3d_parallel_geometry /
+ * _setOS_indices / _set_projection3d_OS_parallel_geometry (astra_wrappers/astra_base.py:
+ * 195-222, 244-255, 287-308) and supp/funcs.py:45-81 (_vec_geom_init3D).
+ *   cos_t, sin_t : host, length na; the caller evaluates them in the dtype of AnglesVec
+ *                  (the reference does np.cos(theta) on the user's array, funcs.py:74-81)
+ *   cor          : host, length na (a scalar CoR is broadcast by the caller)
+ *   os_number    : number of ordered subsets (>=1); subsets are interleaved s, s+os, ...
+ *   quant8       : 1 = round the interpolation fraction to 1/256 like the CUDA texture unit
+ *                  ASTRA samples through (needed for <=1e-4 parity), 0 = exact fp32 weights
+ */
+tmb_geom *tmb_geom_create(int nz, int n, int nu, int na, const double *cos_t, const double *sin_t,
+                          const double *cor, int os_number, int quant8);
+void tmb_geom_destroy(tmb_geom *g);
+/* number of angles in `subset` (-1 = all angles) */
+int tmb_geom_subset_size(const tmb_geom *g, int subset);
+/* reference-format subset table row: newInd_Vec[subset,:] zero padded to bins (astra_base.py:195-209) */
+int tmb_geom_subset_row(const tmb_geom *g, int subset, int *out_bins /* [ceil(na/os)] */);
+/* the fp32 per-angle table the kernels read from constant memory: out[na][8] (host) */
+int tmb_geom_table(const tmb_geom *g, float *out);
+/* bytes of device scratch tmb_fp3d / tmb_bp3d / tmb_grad need.  The caller allocates it ONCE,
+ * zero-fills it ONCE (the kernels keep the zero borders intact) and passes it to every call. */
+size_t tmb_geom_workspace_bytes(const tmb_geom *g);
+
+/* ---- projector pair --------------------------------------------------------------------
+ * tmb_fp3d replaces AstraBase.runAstraProj3DCuPy -> astra direct_FP3D (astra_base.py:560-606)
+ *          i.e. AstraTools3D._forwprojCuPy/_forwprojOSCuPy (astra_tools3d.py:78-86)
+ * tmb_bp3d replaces AstraBase.runAstraBackproj3DCuPy -> direct_BP3D (astra_base.py:518-558)
+ *          i.e. AstraTools3D._backprojCuPy/_backprojOSCuPy (astra_tools3d.py:102-110)
+ * subset = -1: all angles, sino is [nz][na][nu]; otherwise sino is [nz][subset_size][nu].
+ */
+int tmb_fp3d(tmb_geom *g, int subset, const float *vol, float *sino, void *workspace, void *stream);
+int tmb_bp3d(tmb_geom *g, int subset, const float *sino, float *vol, void *workspace, void *stream);
+
+/* Fused gradient of the data term (data_fidelities.py:7-40):
+ *   grad = A_s^T ( W .* (A_s x - b_s) )          LS / PWLS
+ *   grad = A_s^T ( 1 - b_s / max(A_s x, 1e-8) )  KL
+ * b (and w, or NULL) are the FULL sinograms [nz][na][nu]; the subset rows are picked inside
+ * the forward projector's epilogue (replaces the b[:, indVec, :] gather copy of
+ * methodsIR_CuPy.py:454-457 and the temporaries of data_fidelities.py:30-39).             */
+int tmb_grad(tmb_geom *g, int subset, int fidelity, const float *x, const float *b, const float *w,
+             float *grad, void *workspace, void *stream);
+
+/* ---- TV proximal operators ---------------------------------------------------------------
+ * tmb_pd_tv  replaces PD_TV_cupy  (regularisersCuPy.py:170-296 + primal_dual_for_total_variation.cu)
+ * tmb_rof_tv replaces ROF_TV_cupy (regularisersCuPy.py:41-167 + rudin_osher_fatemi_total_variation.cu)
+ * dims: dz = 1 selects the 2-D kernels (regularisersCuPy.py:299-315 squeezes unit axes on the host).
+ * `out` receives the result (may not alias `in`).  scratch: tmb_tv_workspace_bytes().           */
+size_t tmb_tv_workspace_bytes(int method /*0 PD, 1 ROF*/, int dz, int dy, int dx, int half_precision);
+int tmb_pd_tv(const float *in, float *out, int dz, int dy, int dx, float regularisation_parameter,
+              int iterations, int methodTV, int nonneg, float lipschitz_const, int half_precision,
+              void *workspace, void *stream);
+int tmb_rof_tv(const float *in, float *out, int dz, int dy, int dx, float regularisation_parameter,
+               int iterations, float time_marching_parameter, int half_precision, void *workspace,
+               void *stream);
+
+/* ---- fused elementwise steps of the iterative loops ---------------------------------------
+ * FISTA (methodsIR_CuPy.py:463-468):  X = X_t - Linv * grad ; optional max(X, 0)             */
+int tmb_fista_grad_step(const float *x_t, const float *grad, float *x, size_t count, float l_inv,
+                        int nonneg, void *stream);
+/* FISTA (methodsIR_CuPy.py:475):  X_t = X + coef * (X - X_old)                              */
+int tmb_fista_momentum(const float *x, const float *x_old, float *x_t, size_t count, float coef,
+                       void *stream);
+/* ADMM z-update (methodsIR_CuPy.py:545-557): z -= tau*(grad + rho*(z - x + u)); optional
+ * max(z,0); optional relaxation z = (1-alpha) z_old + alpha z; z_old = z; xprox = z + u     */
+int tmb_admm_z_step(float *z, float *z_old, const float *x, const float *u, const float *grad,
+                    float *xprox, size_t count, float tau, float rho, int nonneg, int relax,
+                    float alpha, void *stream);
+/* ADMM dual update (methodsIR_CuPy.py:566): u += z - x                                        */
+int tmb_admm_u_step(float *u, const float *z, const float *x, size_t count, void *stream);
+/* y = a*x + y-like helpers used by Landweber/SIRT/CGLS (methodsIR_CuPy.py:164-166,211-216,279-289) */
+int tmb_axpy(float a, const float *x, float *y, size_t count, int nonneg, void *stream);
+
+/* ---- FBP filter ---------------------------------------------------------------------------
+ * Builds the half-spectrum sinc filter of generate_filtersync.cu:5-82 (fourier.py:52-66):
+ * f[n/2+1], device pointer.                                                                   */
+int tmb_sinc_filter(float cutoff, float *f, int n, float multiplier, void *stream);
+/* spectrum *= filter, in place; spec is interleaved complex64 [rows][n/2+1] (fourier.py:69)    */
+int tmb_apply_filter(float *spec, const float *f, size_t rows, int nbins, void *stream);
+/* circular mask (supp/suppTools.py:364-396), in place on vol[nz][n][n]                        */
+int tmb_circular_mask(float *vol, int nz, int n, float radius, void *stream);
+
+/* ---- host-buffer entry points (what a non-CUDA caller binds; H2D/D2H inside) --------------- */
+int tmb_fp3d_host(tmb_geom *g, int subset, const float *vol_host, float *sino_host);
+int tmb_bp3d_host(tmb_geom *g, int subset, const float *sino_host, float *vol_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMB_H */

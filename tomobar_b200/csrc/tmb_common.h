@@ -1,0 +1,78 @@
+// Internal helpers shared by the libtmb translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/tmb.h"
+
+namespace tmb {
+
+void set_error(const std::string &msg);
+
+#define TMB_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::tmb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+      return TMB_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define TMB_REQUIRE(cond, msg)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::tmb::set_error(msg);                                                              \
+      return TMB_ERR_ARG;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+// Launch-error check that does not synchronise.
+inline int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return TMB_ERR_CUDA;
+  }
+  return TMB_OK;
+}
+
+// ---- interior layouts ---------------------------------------------------------------------
+// z is blocked in chunks of 4 slices so that one smem/global element is a float4 (16 B):
+//   S_int[zc][a][SPAD + u + SPAD]   sinogram lines, zero borders of SPAD elements
+//   V1  [zc][r][VPAD + c + VPAD]    volume rows    (lines = rows,    interpolate along columns)
+//   V0  [zc][c][VPAD + r + VPAD]    volume columns (lines = columns, interpolate along rows)
+// The zero borders implement ASTRA's "zero outside" addressing and make every TMA window a
+// plain in-bounds contiguous bulk copy.
+constexpr int ZC = 4;         // slices per z-chunk (float4)
+constexpr int NZC = 2;        // z-chunks per CTA
+constexpr int BP_W = 48;      // sinogram window (elements) of a 32x32 voxel tile
+constexpr int SPAD = BP_W;    // zero border of S_int
+constexpr int FP_K = 128;     // detector bins per CTA in the forward projector
+constexpr int FP_W = 184;     // volume-line window of FP_K bins: ceil(127*sqrt(2)) + 4
+constexpr int VPAD = FP_W;    // zero border of V0 / V1
+constexpr int MAX_ANGLES = 2000;  // constant-memory table capacity (2 x float4 per angle)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct GeomDims {
+  int nz, n, nu, na;
+  int nzc;   // z-chunks allocated (multiple of NZC)
+  int up;    // nu + 2*SPAD
+  int qp;    // n + 2*VPAD
+};
+
+}  // namespace tmb
+
+// Geometry object behind the opaque handle.
+struct tmb_geom {
+  tmb::GeomDims d;
+  int os_number;
+  int quant8;
+  int bins;                 // ceil(na / os)
+  float *table;             // host [na][8]
+  uint64_t id;              // identity for the constant-memory cache
+  // workspace carve-up (bytes offsets)
+  size_t off_v0, off_v1, off_s, ws_bytes;
+};

@@ -1,0 +1,188 @@
+// Fused elementwise steps of the iterative loops, FBP filter construction, circular mask.
+// All of these are single-pass HBM streams; 128-bit accesses where alignment allows.
+#include "tmb_common.h"
+
+namespace tmb {
+
+constexpr int EL_THREADS = 256;
+
+static inline int el_blocks(size_t count) {
+  size_t b = (count + EL_THREADS - 1) / EL_THREADS;
+  const size_t cap = 148 * 16;  // grid-stride: 16 resident CTAs on each of the 148 SMs
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+// X = X_t - Linv*grad, optional clamp   (methodsIR_CuPy.py:463-468)
+// (x may alias g: every element is read before it is written)
+__global__ void k_fista_grad_step(const float *__restrict__ xt, const float *g, float *x,
+                                  size_t n, float linv, int nonneg) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // separate multiply and subtract (two roundings) like the reference's two array ops
+    float v = __fsub_rn(xt[i], __fmul_rn(linv, g[i]));
+    if (nonneg) v = fmaxf(v, 0.f);
+    x[i] = v;
+  }
+}
+
+// X_t = X + coef*(X - X_old)   (methodsIR_CuPy.py:475)
+__global__ void k_fista_momentum(const float *__restrict__ x, const float *__restrict__ xo, float *__restrict__ xt,
+                                 size_t n, float coef) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = x[i];
+    xt[i] = __fadd_rn(a, __fmul_rn(coef, __fsub_rn(a, xo[i])));
+  }
+}
+
+// ADMM z-update, relaxation, z_old copy and prox input in one pass (methodsIR_CuPy.py:545-557)
+__global__ void k_admm_z(float *__restrict__ z, float *__restrict__ zo, const float *__restrict__ x,
+                         const float *__restrict__ u, const float *__restrict__ g, float *__restrict__ xp, size_t n,
+                         float tau, float rho, int nonneg, int relax, float alpha, float oma) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float zi = z[i];
+    const float ui = u[i];
+    const float ga = __fmul_rn(rho, __fadd_rn(__fsub_rn(zi, x[i]), ui));
+    zi = __fsub_rn(zi, __fmul_rn(tau, __fadd_rn(g[i], ga)));
+    if (nonneg) zi = fmaxf(zi, 0.f);
+    if (relax) zi = __fadd_rn(__fmul_rn(oma, zo[i]), __fmul_rn(alpha, zi));
+    z[i] = zi;
+    zo[i] = zi;
+    xp[i] = __fadd_rn(zi, ui);
+  }
+}
+
+__global__ void k_admm_u(float *__restrict__ u, const float *__restrict__ z, const float *__restrict__ x, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    u[i] = __fadd_rn(u[i], __fsub_rn(z[i], x[i]));
+}
+
+__global__ void k_axpy(float a, const float *__restrict__ x, float *__restrict__ y, size_t n, int nonneg) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = __fadd_rn(y[i], __fmul_rn(a, x[i]));
+    if (nonneg) v = fmaxf(v, 0.f);
+    y[i] = v;
+  }
+}
+
+// ---- sinc filter (generate_filtersync.cu:5-82) ----------------------------------------------
+__device__ float block_sum(float v, float *sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+
+__global__ void k_sinc_filter(float a, float *__restrict__ f, int n, float multiplier) {
+  __shared__ float sh[32];
+  const float pi = 3.1415926535897932384626433832795f;
+  const float dw = 2 * pi / n;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float rd = a * (-pi + i * dw) / 2.0f;
+    s += rd * rd;
+  }
+  const float sum_sq = block_sum(s, sh);
+  float d = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float rd = a * (-pi + i * dw) / 2.0f;
+    d += sinf(rd) * rd / sum_sq;
+  }
+  const float dot = block_sum(d, sh);
+  const float dot_sq = dot * dot;
+  const int shift = n / 2;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int o = (i + shift) % n;  // ifftshifted position; keep the rfft half
+    if (o >= n / 2 + 1) continue;
+    const float rd = a * (-pi + i * dw) / 2.0f;
+    const float r = fabsf((float)(2.0 / (double)a * (double)sinf(rd))) * dot_sq;
+    f[o] = r * multiplier;
+  }
+}
+
+__global__ void k_apply_filter(float2 *__restrict__ spec, const float *__restrict__ f, size_t rows, int nbins) {
+  const size_t total = rows * (size_t)nbins;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float w = __ldg(f + (i % nbins));
+    float2 v = spec[i];
+    v.x *= w;
+    v.y *= w;
+    spec[i] = v;
+  }
+}
+
+// circular mask (supp/suppTools.py:364-396)
+__global__ void k_mask(float *__restrict__ vol, int nz, int n, double limit) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= n) return;
+  const int h = n / 2;
+  const double dist = sqrt((double)((c - h) * (c - h) + (r - h) * (r - h)));
+  if (dist <= limit) return;
+  for (int z = blockIdx.z; z < nz; z += gridDim.z) vol[((size_t)z * n + r) * n + c] = 0.f;
+}
+
+}  // namespace tmb
+
+using namespace tmb;
+
+extern "C" int tmb_fista_grad_step(const float *x_t, const float *grad, float *x, size_t count, float l_inv,
+                                   int nonneg, void *stream) {
+  TMB_REQUIRE(x_t && grad && x, "tmb_fista_grad_step: null argument");
+  k_fista_grad_step<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(x_t, grad, x, count, l_inv, nonneg);
+  return check_launch("k_fista_grad_step");
+}
+
+extern "C" int tmb_fista_momentum(const float *x, const float *x_old, float *x_t, size_t count, float coef,
+                                  void *stream) {
+  TMB_REQUIRE(x && x_old && x_t, "tmb_fista_momentum: null argument");
+  k_fista_momentum<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(x, x_old, x_t, count, coef);
+  return check_launch("k_fista_momentum");
+}
+
+extern "C" int tmb_admm_z_step(float *z, float *z_old, const float *x, const float *u, const float *grad,
+                               float *xprox, size_t count, float tau, float rho, int nonneg, int relax, float alpha,
+                               void *stream) {
+  TMB_REQUIRE(z && z_old && x && u && grad && xprox, "tmb_admm_z_step: null argument");
+  k_admm_z<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(z, z_old, x, u, grad, xprox, count, tau, rho,
+                                                                      nonneg, relax, alpha,
+                                                                      (float)(1.0 - (double)alpha));
+  return check_launch("k_admm_z");
+}
+
+extern "C" int tmb_admm_u_step(float *u, const float *z, const float *x, size_t count, void *stream) {
+  TMB_REQUIRE(u && z && x, "tmb_admm_u_step: null argument");
+  k_admm_u<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(u, z, x, count);
+  return check_launch("k_admm_u");
+}
+
+extern "C" int tmb_axpy(float a, const float *x, float *y, size_t count, int nonneg, void *stream) {
+  TMB_REQUIRE(x && y, "tmb_axpy: null argument");
+  k_axpy<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(a, x, y, count, nonneg);
+  return check_launch("k_axpy");
+}
+
+extern "C" int tmb_sinc_filter(float cutoff, float *f, int n, float multiplier, void *stream) {
+  TMB_REQUIRE(f && n >= 2, "tmb_sinc_filter: bad argument");
+  k_sinc_filter<<<1, 256, 0, (cudaStream_t)stream>>>(cutoff, f, n, multiplier);
+  return check_launch("k_sinc_filter");
+}
+
+extern "C" int tmb_apply_filter(float *spec, const float *f, size_t rows, int nbins, void *stream) {
+  TMB_REQUIRE(spec && f && nbins >= 1, "tmb_apply_filter: bad argument");
+  k_apply_filter<<<el_blocks(rows * (size_t)nbins), EL_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float2 *>(spec), f, rows, nbins);
+  return check_launch("k_apply_filter");
+}
+
+extern "C" int tmb_circular_mask(float *vol, int nz, int n, float radius, void *stream) {
+  TMB_REQUIRE(vol && nz >= 1 && n >= 1 && radius > 0.f, "tmb_circular_mask: bad argument");
+  const int h = n / 2;
+  // python: h - abs(h - h/radius)  (radius <= 1)   or   h + abs(h - h/radius)
+  const double delta = fabs((double)h - (double)h / (double)radius);
+  const double limit = radius <= 1.0f ? (double)h - delta : (double)h + delta;
+  dim3 grid((n + 127) / 128, n, nz < 64 ? nz : 64);
+  k_mask<<<grid, 128, 0, (cudaStream_t)stream>>>(vol, nz, n, limit);
+  return check_launch("k_mask");
+}

@@ -1,0 +1,578 @@
+// 3-D parallel-beam projector pair for sm_100a.
+//
+// Replaces astra-toolbox's par3d kernels that the reference reaches through
+// astra_wrappers/astra_base.py:554 (direct_BP3D) and :601 (direct_FP3D).
+//
+// Both operators have the same shape:
+//     out[item][z] = sum over lines  lerp( IN[line][ pos(item, line) ][z] )
+//   back-projection : items = voxels of a 32x32 tile, lines = angles,       IN = sinogram
+//   forward (Joseph): items = 128 detector bins of one angle, lines = the N volume rows
+//                     (or columns) the ray marches through,                 IN = volume
+// The interpolation index and weight depend on (item, line) only -- never on z -- so each
+// thread computes them once and applies them to 8 slices (two float4 z-chunks).  The part
+// of every line a CTA needs is a contiguous window of the z-blocked interior layout; a
+// producer warp streams these windows into a shared-memory ring with cp.async.bulk (TMA,
+// SASS UBLKCP) completing on mbarriers, the consumer warps read them with LDS.128.
+// Per-angle constants live in __constant__ memory.
+#include "tmb_common.h"
+
+namespace tmb {
+
+// ------------------------------------------------------------------------------------------
+// constant-memory angle table (uploaded once per geometry, see ensure_table)
+//   c_bp[a] = (cos, sin, bp_off, 0)
+//   c_fp[a] = (alpha, b0, bstep, +-scale)   sign(scale) < 0 <=> dir 0 (march along columns)
+// ------------------------------------------------------------------------------------------
+__constant__ float4 c_bp[MAX_ANGLES];
+__constant__ float4 c_fp[MAX_ANGLES];
+
+static uint64_t g_loaded_geom[64] = {0};  // per device: which table chunk sits in constant memory
+
+int ensure_table(const tmb_geom *g, int a_begin, int a_count, cudaStream_t st) {
+  // table chunk [a_begin, a_begin + a_count) of geometry g -> constant memory slots [0, a_count)
+  static thread_local float4 hbp[MAX_ANGLES], hfp[MAX_ANGLES];
+  int dev = 0;
+  TMB_CUDA_CHECK(cudaGetDevice(&dev));
+  uint64_t key = g->id * 4096u + (uint64_t)(a_begin / MAX_ANGLES);
+  if (g_loaded_geom[dev & 63] == key) return TMB_OK;
+  // the previous upload's staging buffer may still be in flight on another geometry: the
+  // copies below are synchronous w.r.t. the host for pageable memory, so reuse is safe.
+  for (int i = 0; i < a_count; ++i) {
+    const float *t = g->table + (size_t)(a_begin + i) * 8;
+    hbp[i] = make_float4(t[0], t[1], t[2], 0.f);
+    hfp[i] = make_float4(t[3], t[4], t[5], t[7] == 0.f ? -t[6] : t[6]);
+  }
+  TMB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_bp, hbp, sizeof(float4) * a_count, 0, cudaMemcpyHostToDevice, st));
+  TMB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_fp, hfp, sizeof(float4) * a_count, 0, cudaMemcpyHostToDevice, st));
+  g_loaded_geom[dev & 63] = key;
+  return TMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (PTX)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void lerp_acc(float4 &acc, float g, float f, const float4 &s0, const float4 &s1) {
+  acc.x = fmaf(g, s0.x, acc.x); acc.x = fmaf(f, s1.x, acc.x);
+  acc.y = fmaf(g, s0.y, acc.y); acc.y = fmaf(f, s1.y, acc.y);
+  acc.z = fmaf(g, s0.z, acc.z); acc.z = fmaf(f, s1.z, acc.z);
+  acc.w = fmaf(g, s0.w, acc.w); acc.w = fmaf(f, s1.w, acc.w);
+}
+
+__device__ __forceinline__ float frac_weight(float f, int quant) {
+  // CUDA texture units hold the interpolation fraction in 1.8 fixed point
+  return quant ? rintf(f * 256.0f) * (1.0f / 256.0f) : f;
+}
+
+// ==========================================================================================
+// layout conversion kernels (HBM-bound; a few ms next to seconds of projector work)
+// ==========================================================================================
+// sino[nz][na][nu] -> S_int[nzc][na][up] (float4 over 4 slices), interior only
+__global__ void k_sino_to_int(const float *__restrict__ sino, float4 *__restrict__ sint, int nz, int na, int nu,
+                              int up) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  const int zc = blockIdx.z;
+  if (u >= nu) return;
+  float v[ZC];
+#pragma unroll
+  for (int j = 0; j < ZC; ++j) {
+    const int z = zc * ZC + j;
+    v[j] = z < nz ? sino[((size_t)z * na + a) * nu + u] : 0.f;
+  }
+  sint[((size_t)zc * na + a) * up + SPAD + u] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// vol[nz][n][n] -> V1[nzc][r][qp] (rows) and V0[nzc][c][qp] (columns, via a smem transpose)
+__global__ void k_vol_to_int(const float *__restrict__ vol, float4 *__restrict__ v0, float4 *__restrict__ v1, int nz,
+                             int n, int qp, int want0, int want1) {
+  __shared__ float4 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, zc = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    float v[ZC] = {0.f, 0.f, 0.f, 0.f};
+    if (r < n && c < n) {
+#pragma unroll
+      for (int k = 0; k < ZC; ++k) {
+        const int z = zc * ZC + k;
+        if (z < nz) v[k] = vol[((size_t)z * n + r) * n + c];
+      }
+    }
+    const float4 q = make_float4(v[0], v[1], v[2], v[3]);
+    tile[j][tx] = q;
+    if (want1 && r < n && c < n) v1[((size_t)zc * n + r) * qp + VPAD + c] = q;
+  }
+  if (!want0) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < n && c < n) v0[((size_t)zc * n + c) * qp + VPAD + r] = tile[tx][j];
+  }
+}
+
+// ==========================================================================================
+// back-projection  (voxel-driven)
+// ==========================================================================================
+constexpr int BP_G = 8;       // angles per pipeline stage
+constexpr int BP_STAGES = 3;
+constexpr int BP_CONSUMERS = 256;
+constexpr int BP_VPT = 4;     // voxels per thread (32x32 tile / 256 threads)
+
+struct BpArgs {
+  const float4 *sint;  // S_int of the angles being back-projected: [nzc][na_loc][up]
+  float *vol;          // [nz][n][n]
+  int n, nu, up, nz, na_loc;
+  int a_first, a_stride;  // constant-table index of local angle j: a_first + j*a_stride
+  int j_begin, j_count;   // local angle range handled by this launch
+  int accumulate;         // 1: start from the values already in vol
+  int quant;
+};
+
+__global__ void __launch_bounds__(BP_CONSUMERS + 32) k_bp(const BpArgs p) {
+  __shared__ __align__(128) float4 buf[BP_STAGES][BP_G][NZC][BP_W];
+  __shared__ int wst[BP_STAGES][BP_G];
+  __shared__ __align__(8) uint64_t full_bar[BP_STAGES], empty_bar[BP_STAGES];
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, zc0 = blockIdx.z * NZC;
+  const float half = 0.5f * (float)p.n;
+
+  if (tid == 0) {
+    for (int s = 0; s < BP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], BP_CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int n_iter = (p.j_count + BP_G - 1) / BP_G;
+
+  if (tid >= BP_CONSUMERS) {
+    // ---------------- producer warp: one elected lane drives the TMA engine -----------------
+    if (tid == BP_CONSUMERS) {
+      const float xa = (float)x0 - half + 0.5f, xb = (float)(x0 + 31) - half + 0.5f;
+      const float ya = (float)y0 - half + 0.5f, yb = (float)(y0 + 31) - half + 0.5f;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % BP_STAGES;
+        const uint32_t ph = (it / BP_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int j0 = p.j_begin + it * BP_G;
+        const int ng = min(BP_G, p.j_begin + p.j_count - j0);
+        for (int ga = 0; ga < ng; ++ga) {
+          const float4 t = c_bp[p.a_first + (j0 + ga) * p.a_stride];
+          const float mn = t.z + fminf(xa * t.x, xb * t.x) + fminf(ya * t.y, yb * t.y);
+          int ws = (int)floorf(mn) - 1;
+          ws = max(-SPAD, min(ws, p.nu));
+          wst[s][ga] = ws;
+        }
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * NZC * BP_W * sizeof(float4)));
+        for (int ga = 0; ga < ng; ++ga) {
+          const int ws = wst[s][ga];
+#pragma unroll
+          for (int c = 0; c < NZC; ++c) {
+            const float4 *src = p.sint + ((size_t)(zc0 + c) * p.na_loc + (j0 + ga)) * p.up + (SPAD + ws);
+            bulk_g2s(&buf[s][ga][c][0], src, BP_W * sizeof(float4), &full_bar[s]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: 8 warps, each lane owns 4 voxels x 8 slices -------------------
+  const int warp = tid >> 5, lane = tid & 31;
+  float vx[BP_VPT], vy[BP_VPT];
+  int ix[BP_VPT], iy[BP_VPT];
+  float4 acc[BP_VPT][NZC];
+#pragma unroll
+  for (int j = 0; j < BP_VPT; ++j) {
+    const int patch = warp * BP_VPT + j;  // 32 patches of 8(x) x 4(y) voxels
+    ix[j] = x0 + (patch & 3) * 8 + (lane & 7);
+    iy[j] = y0 + (patch >> 2) * 4 + (lane >> 3);
+    vx[j] = (float)ix[j] - half + 0.5f;
+    vy[j] = (float)iy[j] - half + 0.5f;
+#pragma unroll
+    for (int c = 0; c < NZC; ++c) acc[j][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (p.accumulate) {
+#pragma unroll
+    for (int j = 0; j < BP_VPT; ++j) {
+      if (ix[j] < p.n && iy[j] < p.n) {
+#pragma unroll
+        for (int c = 0; c < NZC; ++c) {
+          float *a4 = reinterpret_cast<float *>(&acc[j][c]);
+#pragma unroll
+          for (int k = 0; k < ZC; ++k) {
+            const int z = (zc0 + c) * ZC + k;
+            if (z < p.nz) a4[k] = p.vol[((size_t)z * p.n + iy[j]) * p.n + ix[j]];
+          }
+        }
+      }
+    }
+  }
+
+  for (int it = 0; it < n_iter; ++it) {
+    const int s = it % BP_STAGES;
+    const uint32_t ph = (it / BP_STAGES) & 1;
+    mbar_wait(&full_bar[s], ph);
+    const int j0 = p.j_begin + it * BP_G;
+    const int ng = min(BP_G, p.j_begin + p.j_count - j0);
+    for (int ga = 0; ga < ng; ++ga) {
+      const float4 t = c_bp[p.a_first + (j0 + ga) * p.a_stride];
+      const int ws = wst[s][ga];
+#pragma unroll
+      for (int j = 0; j < BP_VPT; ++j) {
+        const float u = fmaf(vx[j], t.x, fmaf(vy[j], t.y, t.z));
+        const float fl = floorf(u);
+        const float f = frac_weight(u - fl, p.quant);
+        const float g = 1.0f - f;
+        int i = (int)fl - ws;
+        i = max(0, min(i, BP_W - 2));
+#pragma unroll
+        for (int c = 0; c < NZC; ++c) {
+          const float4 s0 = buf[s][ga][c][i];
+          const float4 s1 = buf[s][ga][c][i + 1];
+          lerp_acc(acc[j][c], g, f, s0, s1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // epilogue: each warp stores 4 rows x 8 columns (one 32-B sector per row) per slice
+#pragma unroll
+  for (int j = 0; j < BP_VPT; ++j) {
+    if (ix[j] < p.n && iy[j] < p.n) {
+#pragma unroll
+      for (int c = 0; c < NZC; ++c) {
+        const float *a4 = reinterpret_cast<const float *>(&acc[j][c]);
+#pragma unroll
+        for (int k = 0; k < ZC; ++k) {
+          const int z = (zc0 + c) * ZC + k;
+          if (z < p.nz) p.vol[((size_t)z * p.n + iy[j]) * p.n + ix[j]] = a4[k];
+        }
+      }
+    }
+  }
+}
+
+// ==========================================================================================
+// forward projection  (Joseph)
+// ==========================================================================================
+constexpr int FP_G = 4;       // volume lines per pipeline stage
+constexpr int FP_STAGES = 3;
+
+struct FpArgs {
+  const float4 *v0;  // [nzc][n][qp]  lines = columns
+  const float4 *v1;  // [nzc][n][qp]  lines = rows
+  float *sino;       // mode 0: API layout [nz][na_loc][nu]
+  float4 *sint;      // mode 1: residual written straight into S_int [nzc][na_loc][up]
+  const float *b;    // mode 1: full data sinogram [nz][na_tot][nu]
+  const float *w;    // mode 1: PWLS weights (same layout) or nullptr
+  int n, nu, up, qp, nz, na_loc, na_tot;
+  int a_first, a_stride;  // constant-table slot of local angle j
+  int g_first, g_stride;  // global angle index (row of b / w) of local angle j
+  int j_begin;            // local angle of blockIdx.y == 0
+  int mode;               // 0 plain projection, 1 fused residual epilogue
+  int fidelity;
+  int quant;
+};
+
+__global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
+  extern __shared__ __align__(128) unsigned char fp_smem[];
+  float4(*buf)[FP_G][NZC][FP_W] = reinterpret_cast<float4(*)[FP_G][NZC][FP_W]>(fp_smem);
+  __shared__ int wst[FP_STAGES][FP_G];
+  __shared__ __align__(8) uint64_t full_bar[FP_STAGES], empty_bar[FP_STAGES];
+
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * FP_K;
+  const int j = p.j_begin + blockIdx.y;  // local angle
+  const int zc0 = blockIdx.z * NZC;
+  const float4 t = c_fp[p.a_first + j * p.a_stride];
+  const float alpha = t.x, b0 = t.y, bstep = t.z;
+  const float scale = fabsf(t.w);
+  const float4 *vsrc = (t.w < 0.f) ? p.v0 : p.v1;
+  const float half = 0.5f * (float)p.n;
+
+  if (tid == 0) {
+    for (int s = 0; s < FP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], FP_K / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int n_iter = (p.n + FP_G - 1) / FP_G;
+
+  if (tid >= FP_K) {
+    if (tid == FP_K) {
+      const float beta_a = fmaf((float)k0, bstep, b0);
+      const float beta_b = fmaf((float)(k0 + FP_K - 1), bstep, b0);
+      const float beta_min = fminf(beta_a, beta_b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % FP_STAGES;
+        const uint32_t ph = (it / FP_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int m0 = it * FP_G;
+        const int ng = min(FP_G, p.n - m0);
+        for (int gm = 0; gm < ng; ++gm) {
+          const float xm = (float)(m0 + gm) - half + 0.5f;
+          int ws = (int)floorf(fmaf(alpha, xm, beta_min)) - 1;
+          ws = max(-VPAD, min(ws, p.n));
+          wst[s][gm] = ws;
+        }
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * NZC * FP_W * sizeof(float4)));
+        for (int gm = 0; gm < ng; ++gm) {
+          const int ws = wst[s][gm];
+#pragma unroll
+          for (int c = 0; c < NZC; ++c) {
+            const float4 *src = vsrc + ((size_t)(zc0 + c) * p.n + (m0 + gm)) * p.qp + (VPAD + ws);
+            bulk_g2s(&buf[s][gm][c][0], src, FP_W * sizeof(float4), &full_bar[s]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  const int lane = tid & 31;
+  const int k = k0 + tid;
+  const float beta = fmaf((float)k, bstep, b0);
+  float4 acc[NZC];
+#pragma unroll
+  for (int c = 0; c < NZC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int it = 0; it < n_iter; ++it) {
+    const int s = it % FP_STAGES;
+    const uint32_t ph = (it / FP_STAGES) & 1;
+    mbar_wait(&full_bar[s], ph);
+    const int m0 = it * FP_G;
+    const int ng = min(FP_G, p.n - m0);
+    for (int gm = 0; gm < ng; ++gm) {
+      const float xm = (float)(m0 + gm) - half + 0.5f;
+      const float rho = fmaf(alpha, xm, beta);
+      const float fl = floorf(rho);
+      const float f = frac_weight(rho - fl, p.quant);
+      const float g = 1.0f - f;
+      int i = (int)fl - wst[s][gm];
+      i = max(0, min(i, FP_W - 2));
+#pragma unroll
+      for (int c = 0; c < NZC; ++c) {
+        const float4 s0 = buf[s][gm][c][i];
+        const float4 s1 = buf[s][gm][c][i + 1];
+        lerp_acc(acc[c], g, f, s0, s1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  if (k >= p.nu) return;
+#pragma unroll
+  for (int c = 0; c < NZC; ++c) {
+    float *a4 = reinterpret_cast<float *>(&acc[c]);
+    if (p.mode == 0) {
+#pragma unroll
+      for (int q = 0; q < ZC; ++q) {
+        const int z = (zc0 + c) * ZC + q;
+        if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = a4[q] * scale;
+      }
+    } else {
+      // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
+      const int ga = p.g_first + j * p.g_stride;
+      float r[ZC];
+#pragma unroll
+      for (int q = 0; q < ZC; ++q) {
+        const int z = (zc0 + c) * ZC + q;
+        float v = 0.f;
+        if (z < p.nz) {
+          const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
+          const float ax = a4[q] * scale;
+          if (p.fidelity == TMB_FID_KL) {
+            v = 1.0f - p.b[idx] / fmaxf(ax, 1e-8f);
+          } else {
+            v = ax - p.b[idx];
+            if (p.w != nullptr) v *= p.w[idx];
+          }
+        }
+        r[q] = v;
+      }
+      p.sint[((size_t)(zc0 + c) * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// ==========================================================================================
+// host-side launchers
+// ==========================================================================================
+static int subset_first(const tmb_geom *g, int subset) { return subset < 0 ? 0 : subset; }
+static int subset_stride(const tmb_geom *g, int subset) { return subset < 0 ? 1 : g->os_number; }
+int subset_size(const tmb_geom *g, int subset) {
+  if (subset < 0) return g->d.na;
+  return (g->d.na - subset + g->os_number - 1) / g->os_number;
+}
+
+static int launch_sino_to_int(const tmb_geom *g, const float *sino, float4 *sint, int na_loc, cudaStream_t st) {
+  dim3 grid((g->d.nu + 255) / 256, na_loc, g->d.nzc);
+  k_sino_to_int<<<grid, 256, 0, st>>>(sino, sint, g->d.nz, na_loc, g->d.nu, g->d.up);
+  return check_launch("k_sino_to_int");
+}
+
+static int launch_vol_to_int(const tmb_geom *g, const float *vol, float4 *v0, float4 *v1, cudaStream_t st) {
+  dim3 grid((g->d.n + 31) / 32, (g->d.n + 31) / 32, g->d.nzc);
+  k_vol_to_int<<<grid, dim3(32, 8), 0, st>>>(vol, v0, v1, g->d.nz, g->d.n, g->d.qp, 1, 1);
+  return check_launch("k_vol_to_int");
+}
+
+// back-project S_int (na_loc local angles of `subset`) into vol
+static int launch_bp(const tmb_geom *g, int subset, const float4 *sint, float *vol, cudaStream_t st) {
+  const int na_loc = subset_size(g, subset);
+  const int first = subset_first(g, subset), stride = subset_stride(g, subset);
+  BpArgs a;
+  a.sint = sint; a.vol = vol;
+  a.n = g->d.n; a.nu = g->d.nu; a.up = g->d.up; a.nz = g->d.nz; a.na_loc = na_loc;
+  a.quant = g->quant8;
+  dim3 grid((g->d.n + 31) / 32, (g->d.n + 31) / 32, g->d.nzc / NZC);
+  // the constant table holds MAX_ANGLES global angles per upload; chunk the angle loop on it
+  int j = 0;
+  while (j < na_loc) {
+    const int gl = first + j * stride;                   // global angle of local j
+    const int chunk_base = (gl / MAX_ANGLES) * MAX_ANGLES;
+    int cnt = 0;
+    while (j + cnt < na_loc && first + (j + cnt) * stride < chunk_base + MAX_ANGLES) ++cnt;
+    int rc = ensure_table(g, chunk_base, min(MAX_ANGLES, g->d.na - chunk_base), st);
+    if (rc) return rc;
+    a.a_first = gl - chunk_base; a.a_stride = stride;
+    a.j_begin = j; a.j_count = cnt; a.accumulate = (j > 0);
+    // a_first + (j0+ga)*stride is evaluated with j0 relative to j_begin inside the kernel
+    a.a_first -= j * stride;
+    k_bp<<<grid, BP_CONSUMERS + 32, 0, st>>>(a);
+    rc = check_launch("k_bp");
+    if (rc) return rc;
+    j += cnt;
+  }
+  return TMB_OK;
+}
+
+static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const float4 *v1, float *sino, float4 *sint,
+                     const float *b, const float *w, int mode, int fidelity, cudaStream_t st) {
+  const int na_loc = subset_size(g, subset);
+  const int first = subset_first(g, subset), stride = subset_stride(g, subset);
+  FpArgs a;
+  a.v0 = v0; a.v1 = v1; a.sino = sino; a.sint = sint; a.b = b; a.w = w;
+  a.n = g->d.n; a.nu = g->d.nu; a.up = g->d.up; a.qp = g->d.qp; a.nz = g->d.nz;
+  a.na_loc = na_loc; a.na_tot = g->d.na;
+  a.g_first = first; a.g_stride = stride;
+  a.mode = mode; a.fidelity = fidelity; a.quant = g->quant8;
+  const size_t smem = sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int j = 0;
+  while (j < na_loc) {
+    const int gl = first + j * stride;
+    const int chunk_base = (gl / MAX_ANGLES) * MAX_ANGLES;
+    int cnt = 0;
+    while (j + cnt < na_loc && first + (j + cnt) * stride < chunk_base + MAX_ANGLES) ++cnt;
+    int rc = ensure_table(g, chunk_base, min(MAX_ANGLES, g->d.na - chunk_base), st);
+    if (rc) return rc;
+    a.a_first = gl - chunk_base - j * stride; a.a_stride = stride;
+    a.j_begin = j;
+    // grid.y is limited to 65535: far above any angle count
+    dim3 grid((g->d.nu + FP_K - 1) / FP_K, cnt, g->d.nzc / NZC);
+    k_fp<<<grid, FP_K + 32, smem, st>>>(a);
+    rc = check_launch("k_fp");
+    if (rc) return rc;
+    j += cnt;
+  }
+  return TMB_OK;
+}
+
+struct Ws {
+  float4 *v0, *v1, *s;
+};
+static Ws carve(const tmb_geom *g, void *workspace) {
+  char *base = static_cast<char *>(workspace);
+  return Ws{reinterpret_cast<float4 *>(base + g->off_v0), reinterpret_cast<float4 *>(base + g->off_v1),
+            reinterpret_cast<float4 *>(base + g->off_s)};
+}
+
+}  // namespace tmb
+
+using namespace tmb;
+
+extern "C" int tmb_fp3d(tmb_geom *g, int subset, const float *vol, float *sino, void *workspace, void *stream) {
+  TMB_REQUIRE(g && vol && sino && workspace, "tmb_fp3d: null argument");
+  TMB_REQUIRE(subset >= -1 && subset < g->os_number, "tmb_fp3d: subset out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws = carve(g, workspace);
+  int rc = launch_vol_to_int(g, vol, ws.v0, ws.v1, st);
+  if (rc) return rc;
+  return launch_fp(g, subset, ws.v0, ws.v1, sino, nullptr, nullptr, nullptr, 0, 0, st);
+}
+
+extern "C" int tmb_bp3d(tmb_geom *g, int subset, const float *sino, float *vol, void *workspace, void *stream) {
+  TMB_REQUIRE(g && vol && sino && workspace, "tmb_bp3d: null argument");
+  TMB_REQUIRE(subset >= -1 && subset < g->os_number, "tmb_bp3d: subset out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws = carve(g, workspace);
+  int rc = launch_sino_to_int(g, sino, ws.s, subset_size(g, subset), st);
+  if (rc) return rc;
+  return launch_bp(g, subset, ws.s, vol, st);
+}
+
+extern "C" int tmb_grad(tmb_geom *g, int subset, int fidelity, const float *x, const float *b, const float *w,
+                        float *grad, void *workspace, void *stream) {
+  TMB_REQUIRE(g && x && b && grad && workspace, "tmb_grad: null argument");
+  TMB_REQUIRE(subset >= -1 && subset < g->os_number, "tmb_grad: subset out of range");
+  TMB_REQUIRE(fidelity >= TMB_FID_LS && fidelity <= TMB_FID_KL, "tmb_grad: unknown fidelity");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws = carve(g, workspace);
+  int rc = launch_vol_to_int(g, x, ws.v0, ws.v1, st);
+  if (rc) return rc;
+  rc = launch_fp(g, subset, ws.v0, ws.v1, nullptr, ws.s, b, fidelity == TMB_FID_PWLS ? w : nullptr, 1, fidelity, st);
+  if (rc) return rc;
+  return launch_bp(g, subset, ws.s, grad, st);
+}
