@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200: ordered-subsets FISTA + PD_TV on the headline geometry of
+BASELINE.json (2048 x 2048 x 512 volume, 1800 angles) plus forward / back-projection rates.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one ordered-subset sub-step of FISTA (subset forward projection with fused residual,
+subset back-projection, gradient step, PD_TV prox, momentum).  `value` is outer FISTA iterations
+per second (= sub-steps/s / OS) for the WHOLE volume; with N GPUs the volume is z-sharded
+(512/N slices per rank, strong scaling, no data-path collective; TV runs per shard like the
+reference's HTTomo z-blocks).  Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HEADLINE = dict(n=2048, nz=512, na=1800, os=24, tv_iters=50, tv_lambda=3e-4)
+METRIC = "fista_os_iterations_per_sec"
+UNIT = "iter/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic input: analytic ellipsoid phantom, closed-form parallel projections, Poisson noise
+# (recipe of the reference's Demos/tomophantom_3D_recon1.py:24-70; TomoPhantom is not installed)
+# ----------------------------------------------------------------------------------------------
+ELLIPSOIDS = [
+    # value, cx, cy, cz, ax, ay, az, phi   (unit cube coordinates in [-1, 1])
+    (1.00, 0.00, 0.00, 0.00, 0.69, 0.92, 0.90, 0.0),
+    (-0.80, 0.00, -0.0184, 0.00, 0.6624, 0.874, 0.88, 0.0),
+    (-0.20, 0.22, 0.00, 0.00, 0.11, 0.31, 0.22, -0.31),
+    (-0.20, -0.22, 0.00, 0.00, 0.16, 0.41, 0.28, 0.31),
+    (0.10, 0.00, 0.35, -0.15, 0.21, 0.25, 0.41, 0.0),
+    (0.10, 0.00, 0.10, 0.25, 0.046, 0.046, 0.05, 0.0),
+    (0.10, -0.08, -0.605, 0.00, 0.046, 0.023, 0.05, 0.0),
+    (0.10, 0.06, -0.605, 0.00, 0.023, 0.046, 0.02, 0.0),
+]
+
+
+def synth_sinogram(torch, nz_total, z0, z1, n, na, device, noise_seed=0, i0=8000.0):
+    """Noisy post-log sinogram [z1-z0, na, n] of the ellipsoid phantom for slices z0..z1-1 of a
+    volume with nz_total slices.  Line integrals are exact (closed form), in pixel units scaled so
+    that the attenuation is O(1)."""
+    angles = torch.linspace(0.0, math.radians(179.9), na, device=device, dtype=torch.float64)
+    t = (torch.arange(n, device=device, dtype=torch.float64) - n / 2 + 0.5) / (n / 2)  # [-1, 1)
+    zs = (torch.arange(z0, z1, device=device, dtype=torch.float64) - nz_total / 2 + 0.5) / (nz_total / 2)
+    sino = torch.zeros((z1 - z0, na, n), device=device, dtype=torch.float32)
+    for (val, cx, cy, cz, ax, ay, az, phi) in ELLIPSOIDS:
+        hz = 1.0 - ((zs - cz) / az) ** 2                       # [z] cross-section scale^2
+        inside = hz > 0
+        sc = torch.sqrt(torch.clamp(hz, min=0.0))             # semi-axes shrink by sc
+        th = angles - phi
+        s2 = (ax * torch.cos(th)) ** 2 + (ay * torch.sin(th)) ** 2          # [a]
+        tau = t[None, :] - (cx * torch.cos(angles) + cy * torch.sin(angles))[:, None]  # [a, u]
+        # chord of the ellipse with semi-axes (ax*sc, ay*sc): 2 ax ay sc^2/s2' * sqrt(s2' - tau^2), s2' = s2 sc^2
+        s2z = s2[None, :, None] * (sc ** 2)[:, None, None]
+        chord = 2.0 * ax * ay * (sc ** 2)[:, None, None] / torch.clamp(s2z, min=1e-30) * torch.sqrt(
+            torch.clamp(s2z - tau[None] ** 2, min=0.0))
+        sino += (val * chord * inside[:, None, None]).to(torch.float32)
+    sino *= 2.0  # attenuation scale: central chord ~ 2*0.2*... O(1)
+    gen = torch.Generator(device=device).manual_seed(noise_seed + z0)
+    counts = torch.poisson(i0 * torch.exp(-sino), generator=gen)
+    sino = -torch.log(torch.clamp(counts, min=1.0) / i0)
+    return sino.contiguous()
+
+
+def synth_sinogram_numpy(nz_total, z0, z1, n, na):
+    import torch
+
+    return synth_sinogram(torch, nz_total, z0, z1, n, na, "cpu").numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (port of the reference's loop + ASTRA's par3d model)
+# on the host cores, bounded sample, scaled linearly in slices x sub-steps
+# ----------------------------------------------------------------------------------------------
+def cpu_fista_substep_rate(cfg, sample_slices=2, repeats=1):
+    from oracle import oracle as O
+
+    n, nz, na, os_n = cfg["n"], cfg["nz"], cfg["na"], cfg["os"]
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    O.build()
+    angles = np.linspace(0.0, math.radians(179.9), na).astype(np.float32)
+    rec = O.RecIR(n, 0, sample_slices, 0.0, angles, n, os_n)
+    b = synth_sinogram_numpy(nz, nz // 2, nz // 2 + sample_slices, n, na)
+    x_t = np.zeros((sample_slices, n, n), np.float32)
+    reg = {"method": "PD_TV", "regul_param": cfg["tv_lambda"], "iterations": cfg["tv_iters"], "methodTV": 0,
+           "PD_LipschitzConstant": 12.0}
+    t_best = float("inf")
+    for r in range(repeats):
+        t0 = time.perf_counter()
+        ind = rec._subset(r % os_n)
+        g = rec.grad_data_term(x_t, b[:, ind, :], True, r % os_n, ind, None, "LS")
+        x = (x_t - np.float32(1e-4) * g).astype(np.float32)
+        x = O.prox_regul(x, reg, 0)
+        x_t = x + np.float32(0.5) * (x - x_t)
+        t_best = min(t_best, time.perf_counter() - t0)
+    # one sub-step on `sample_slices` slices -> one outer iteration on the whole volume
+    t_iter = t_best * (nz / sample_slices) * os_n
+    return 1.0 / t_iter, cores, (f"one OS sub-step (FP+BP of {na // os_n} angles + {cfg['tv_iters']} PD_TV its) on "
+                                 f"{sample_slices} of {nz} slices at N={n}, scaled x{nz // sample_slices} slices "
+                                 f"x{os_n} subsets; {t_best:.2f} s measured")
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, cores, sample = cpu_fista_substep_rate(cfg, sample_slices=2)
+        vals.append(v)
+    v = float(np.median(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / (v * cfg["os"]), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(cfg, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def _config(cfg, gpus):
+    return {
+        "workload": (f"FISTA-OS + PD_TV, volume {cfg['n']}x{cfg['n']}x{cfg['nz']}, {cfg['na']} angles, "
+                     f"OS={cfg['os']}, PD_TV {cfg['tv_iters']} inner iterations (fp32 duals)"),
+        "n": cfg["n"], "nz": cfg["nz"], "angles": cfg["na"], "os_number": cfg["os"],
+        "tv_inner_iterations": cfg["tv_iters"], "z_shards": gpus,
+        "l2_policy": "working set per step (>= 8 GB per rank) far exceeds the 126 MB L2; no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tmb", choices=["tmb", "reference"])
+    ap.add_argument("--n", type=int, default=HEADLINE["n"])
+    ap.add_argument("--nz", type=int, default=HEADLINE["nz"])
+    ap.add_argument("--angles", type=int, default=HEADLINE["na"])
+    ap.add_argument("--os", type=int, default=HEADLINE["os"])
+    ap.add_argument("--tv-iters", type=int, default=HEADLINE["tv_iters"])
+    ap.add_argument("--half", action="store_true", help="fp16 storage of the TV dual variables")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(n=args.n, nz=args.nz, na=args.angles, os=args.os, tv_iters=args.tv_iters,
+               tv_lambda=HEADLINE["tv_lambda"])
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr
+    from tomobar_b200.methodsIR_CuPy import RecToolsIRCuPy
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tomobar_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, nz, na, os_n = cfg["n"], cfg["nz"], cfg["na"], cfg["os"]
+    # z-shard: contiguous block of slices per rank
+    per = (nz + world - 1) // world
+    z0, z1 = min(nz, rank * per), min(nz, (rank + 1) * per)
+    nz_loc = z1 - z0
+    angles = np.linspace(0.0, math.radians(179.9), na).astype(np.float32)
+
+    rec = RecToolsIRCuPy(n, 0, nz_loc, 0.0, angles, n, local_rank, os_n)
+    A = rec.Atools
+    # synthetic data generated on the device, slice blocks of 16 to bound temporaries
+    b = torch.empty((nz_loc, na, n), dtype=torch.float32, device=dev)
+    for s in range(0, nz_loc, 16):
+        e = min(nz_loc, s + 16)
+        b[s:e] = synth_sinogram(torch, nz, z0 + s, z0 + e, n, na, dev)
+    torch.cuda.synchronize()
+
+    reg = {"method": "PD_TV", "regul_param": cfg["tv_lambda"], "iterations": cfg["tv_iters"], "methodTV": 0,
+           "PD_LipschitzConstant": 12.0, "half_precision": bool(args.half)}
+    st = torch.cuda.current_stream(dev).cuda_stream
+    vol_shape = A.vol_geom
+    count = nz_loc * n * n
+    X = torch.zeros(vol_shape, device=dev)
+    X_old = torch.zeros(vol_shape, device=dev)
+    X_t = torch.zeros(vol_shape, device=dev)
+    G = torch.empty(vol_shape, device=dev)
+    L_inv = 1.0 / 2.0e4  # fixed step: the benchmark times the loop, not the power method
+    state = {"t": np.float32(1.0), "sub": 0}
+
+    def substep():
+        nonlocal X, X_old
+        X_old, X = X, X_old
+        t_old = state["t"]
+        A.grad_data_term(X_t, b, state["sub"], "LS", None, out=G)
+        check(lib.tmb_fista_grad_step(ptr(X_t), ptr(G), ptr(G), count, L_inv, 1, st), "grad_step")
+        PD_TV_cupy(G, reg["regul_param"], reg["iterations"], 0, 1, 12.0, local_rank, reg["half_precision"], out=X)
+        t = np.float32((1.0 + np.sqrt(1.0 + 4.0 * t_old ** 2)) * 0.5)
+        check(lib.tmb_fista_momentum(ptr(X), ptr(X_old), ptr(X_t), count, float((t_old - 1.0) / t), st),
+              "momentum")
+        state["t"] = t
+        state["sub"] = (state["sub"] + 1) % os_n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_step = 1 + 1 + 1 + 1 + cfg["tv_iters"] + 1  # layout, FP, BP, step, TV its, momentum
+
+    for _ in range(args.warmup):
+        substep()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        substep()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = 1000.0 / (ms_step * os_n)  # outer iterations per second for the whole (sharded) volume
+
+    # ---- per-kernel timings (CUDA events on the launching stream) ------------------------------
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        c.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(c) / reps
+
+    na_s = A.subset_size(0)
+    sub_sino = torch.empty((nz_loc, na_s, n), device=dev)
+    ms_fp = timed(lambda: check(lib.tmb_fp3d(A._g, 0, ptr(X_t), ptr(sub_sino), ptr(A._workspace()), st), "fp"), 3)
+    ms_bp = timed(lambda: check(lib.tmb_bp3d(A._g, 0, ptr(sub_sino), ptr(G), ptr(A._workspace()), st), "bp"), 3)
+    tv_reps = max(4, cfg["tv_iters"])
+    ms_tv = timed(lambda: PD_TV_cupy(G, reg["regul_param"], tv_reps, 0, 1, 12.0, local_rank,
+                                     reg["half_precision"], out=X), 2) / tv_reps
+    upd_sub = float(nz_loc) * n * n * na_s
+    bytes_tv = (24.0 if args.half else 36.0) * count
+    peak, peak_src = measured_peak_hbm()
+    tv_gbs = bytes_tv / (ms_tv * 1e-3) / 1e9
+    share_tv = ms_tv * cfg["tv_iters"] / ms_step
+    roofline = {
+        "kernel": "k_pd_tv (one Chambolle-Pock iteration)", "bound": "hbm", "achieved": tv_gbs, "peak": peak,
+        "unit": "GB/s", "frac": tv_gbs / peak, "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": bytes_tv, "ms_per_launch": ms_tv, "share_of_step": share_tv,
+    }
+    kernels = {
+        "fp_subset_ms": ms_fp, "bp_subset_ms": ms_bp, "pd_tv_iteration_ms": ms_tv,
+        "fp_gups": upd_sub / (ms_fp * 1e-3) / 1e9, "bp_gups": upd_sub / (ms_bp * 1e-3) / 1e9,
+        "fp_gproj_per_s": float(nz_loc) * na_s * n / (ms_fp * 1e-3) / 1e9 * world,
+        "bp_gproj_per_s": float(nz_loc) * na_s * n / (ms_bp * 1e-3) / 1e9 * world,
+        "lds_roof_gups": 148 * 16 * 1.965e9 / 1e9,
+    }
+
+    # ---- end to end through the public class with HOST buffers -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        del sub_sino
+        b_host = torch.empty(b.shape, dtype=torch.float32, pin_memory=True)
+        b_host.copy_(b)
+        out_host = torch.empty(vol_shape, dtype=torch.float32, pin_memory=True)
+        del X, X_old, X_t, G
+        torch.cuda.empty_cache()
+
+        def e2e_iter():
+            d = b_host.to(dev, non_blocking=True)
+            r = rec.FISTA({"projection_data": d},
+                          {"iterations": 1, "lipschitz_const": 2.0e4, "nonnegativity": True,
+                           "recon_mask_radius": None}, dict(reg))
+            out_host.copy_(r, non_blocking=True)
+
+        e2e_iter()
+        barrier()
+        t0 = time.perf_counter()
+        reps = 1
+        for _ in range(reps):
+            e2e_iter()
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": int(b_host.numel() * 4 / os_n),
+               "d2h_bytes_per_step": int(out_host.numel() * 4 / os_n),
+               "note": "RecToolsIRCuPy.FISTA(iterations=1) from pinned host sinogram to pinned host volume"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_fista_substep_rate(cfg, sample_slices=2)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(cfg, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
