@@ -92,6 +92,10 @@ int tmb_rof_tv(const float *in, float *out, int dz, int dy, int dx, float regula
                int iterations, float time_marching_parameter, int half_precision, void *workspace,
                void *stream);
 
+/* Debug/test switch: 1 routes 3-D TV through the simple one-thread-per-voxel kernels instead of
+ * the z-marching ones (same arithmetic; used by the parity tests).  Returns the old value. */
+int tmb_tv_set_simple_kernels(int enable);
+
 /* ---- fused elementwise steps of the iterative loops ---------------------------------------
  * FISTA (methodsIR_CuPy.py:463-468):  X = X_t - Linv * grad ; optional max(X, 0)             */
 int tmb_fista_grad_step(const float *x_t, const float *grad, float *x, size_t count, float l_inv,

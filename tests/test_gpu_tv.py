@@ -64,3 +64,24 @@ def test_tv_errors_and_edge_cases():
     a = PD_TV_cupy(x, 1e-3, 3)
     b = PD_TV_cupy(x, 1e-3, 4)
     assert torch.equal(x, x0) and not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("shape", [(70, 100, 150), (33, 9, 65), (64, 64, 64)])
+@pytest.mark.parametrize("half", [False, True])
+def test_marching_kernels_match_simple_kernels(shape, half):
+    """The z-marching 3-D kernels and the one-thread-per-voxel kernels share their arithmetic."""
+    from tomobar_b200._lib import lib
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy, ROF_TV_cupy
+
+    v = torch.from_numpy(_vol(shape, 7)).cuda()
+    a = PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half)
+    r = ROF_TV_cupy(v, 3e-4, 9, 1e-3, 0, half)
+    old = lib.tmb_tv_set_simple_kernels(1)
+    try:
+        b = PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half)
+        q = ROF_TV_cupy(v, 3e-4, 9, 1e-3, 0, half)
+    finally:
+        lib.tmb_tv_set_simple_kernels(old)
+    tol = 2e-3 if half else 2e-6
+    assert rel_max(a.cpu().numpy(), b.cpu().numpy()) < tol
+    assert rel_max(r.cpu().numpy(), q.cpu().numpy()) < tol

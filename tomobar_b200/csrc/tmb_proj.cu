@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
 #pragma unroll
       for (int q = 0; q < ZC; ++q) {
         const int z = (zc0 + c) * ZC + q;
-        if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = a4[q] * scale;
+        if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[q], scale);
       }
     } else {
       // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
@@ -427,12 +427,13 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
         float v = 0.f;
         if (z < p.nz) {
           const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
-          const float ax = a4[q] * scale;
+          // explicit roundings: identical to the unfused sequence FP -> subtract -> weight
+          const float ax = __fmul_rn(a4[q], scale);
           if (p.fidelity == TMB_FID_KL) {
-            v = 1.0f - p.b[idx] / fmaxf(ax, 1e-8f);
+            v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
           } else {
-            v = ax - p.b[idx];
-            if (p.w != nullptr) v *= p.w[idx];
+            v = __fsub_rn(ax, p.b[idx]);
+            if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
           }
         }
         r[q] = v;
