@@ -122,6 +122,25 @@ int tmb_apply_filter(float *spec, const float *f, size_t rows, int nbins, void *
 /* circular mask (supp/suppTools.py:364-396), in place on vol[nz][n][n]                        */
 int tmb_circular_mask(float *vol, int nz, int n, float radius, void *stream);
 
+/* ---- FOURIER_INV (USFFT gridding) kernels ----------------------------------------------------
+ * Replace the default centre-gather path of RecToolsDIRCuPy.FOURIER_INV (methodsDIR_CuPy.py:152-447)
+ * and cuda_kernels/fft_us_kernels.cu; the FFTs themselves are cuFFT calls made by the host.
+ * Complex arrays are interleaved float pairs.  nz2 = number of complex slices (= slices / 2).
+ *   tmb_fi_pack       : tmp_p[2*nz2][nproj][n] -> datac[nz2][nproj][n], x (-1)^(x+1)   (r2c_c1dfftshift :529-557)
+ *   tmb_fi_scale_sign : datac *= c * (-1)^(x+1)                                        (c1dfftshift :559-586)
+ *   tmb_fi_gather     : polar samples -> fde[nz2][2n][2n]; theta = -angles (device), sorted_theta /
+ *                       sorted_idx = ascending sort of theta and its permutation (int32)
+ *                       (gather_kernel_center_angle_based_prune :193-319 + gather_kernel_center :468-527)
+ *   tmb_fi_sign2d     : fde *= (-1)^(x+y)                                              (c2dfftshift :588-609)
+ *   tmb_fi_unpad      : crop, de-apodise, unpack re/im -> recon[unpad_z][R][R]         (unpadding_mul_phi :611-657) */
+int tmb_fi_pack(const float *tmp_p, float *datac, int n, int nproj, int nz2, void *stream);
+int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
+int tmb_fi_gather(const float *datac, float *fde, const float *theta, const float *sorted_theta,
+                  const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream);
+int tmb_fi_sign2d(float *fde, int n, int nz2, void *stream);
+int tmb_fi_unpad(float *recon, const float *fde, float mu, int nproj, int unpad_recon_p, int unpad_z,
+                 int unpad_recon_m, int n, int nz2, void *stream);
+
 /* ---- host-buffer entry points (what a non-CUDA caller binds; H2D/D2H inside) --------------- */
 int tmb_fp3d_host(tmb_geom *g, int subset, const float *vol_host, float *sino_host);
 int tmb_bp3d_host(tmb_geom *g, int subset, const float *sino_host, float *vol_host);

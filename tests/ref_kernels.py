@@ -141,3 +141,77 @@ def ref_filtersinc(n, cutoff, multiplier, device="cuda"):
                                          [np.float32(cutoff), f, np.int32(n), np.float32(multiplier)],
                                          shared_mem=256 * 4)
     return f
+
+
+def ref_FOURIER_INV(data, angles, recon_size, cor=0.0, pad=0, filter_type="shepp", cutoff_freq=1.0,
+                    use_naive_prune=False):
+    """Default path of RecToolsDIRCuPy.FOURIER_INV (methodsDIR_CuPy.py:152-447) with the
+    reference's own fft_us_kernels.cu kernels and launch geometry; data [detY, angles, detX]."""
+    import math
+    from tomobar_b200.fourier import calc_filter  # host-side numpy filter (pinned by test_fourier_filters)
+
+    mod = module("fft_us_kernels")
+    dev = data.device
+    nz, nproj, data_n = data.shape
+    odd_h, odd_v = bool(data_n % 2), bool(nz % 2)
+    data_n += odd_h
+    nz += odd_v
+    if odd_h or odd_v:
+        dp = torch.zeros((nz, nproj, data_n), dtype=torch.float32, device=dev)
+        dp[: nz - odd_v, :, : data_n - odd_h] = data
+        dp[: nz - odd_v, :, -int(odd_h)] = data[..., -int(odd_h)]
+        data = dp
+    n = data_n + 2 * pad
+    center_size = min(32768, 2 * n)
+    theta = torch.as_tensor(-np.asarray(angles), dtype=torch.float32, device=dev)
+    sidx = torch.argsort(theta)
+    sth = theta[sidx].contiguous()
+    sth_cpu = sth.cpu().numpy()
+    pi_count = 1 + int(np.ceil(abs(sth_cpu[nproj - 1] - sth_cpu[0]) / math.pi))
+    angle_range = torch.zeros((center_size, center_size, 1 + pi_count * 2), dtype=torch.int16, device=dev)
+    eps = 1e-4
+    mu = -np.log(eps) / (2 * n * n)
+    # filtering (:449-545)
+    over = 2 ** math.ceil(math.log2(data_n * 3))
+    if n > over:
+        over = 2 ** math.ceil(math.log2(n))
+    padding_m = over // 2 - data_n // 2
+    unpad_m, unpad_p = over // 2 - n // 2, over // 2 + n // 2
+    wf = torch.as_tensor(calc_filter(over, filter_type, cutoff_freq), device=dev)
+    t = torch.fft.rfftfreq(over, device=dev).to(torch.float32)
+    w = wf * torch.exp(-2 * np.pi * 1j * t * (cor + 0.5))
+    tmp_p = torch.empty((nz, nproj, n), dtype=torch.float32, device=dev)
+    for z in range(nz):
+        tmp = torch.nn.functional.pad(data[z:z + 1], (padding_m, padding_m), mode="replicate")
+        tmp = torch.fft.irfft(w * torch.fft.rfft(tmp, dim=2), dim=2)
+        tmp_p[z] = tmp[0, :, unpad_m:unpad_p]
+    nz2 = nz // 2
+    datac = torch.empty((nz2, nproj, n), dtype=torch.complex64, device=dev)
+    fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+    i32 = np.int32
+    cdiv = lambda a, b: int(np.ceil(a / b))
+    mod.launch("r2c_c1dfftshift", (cdiv(n, 32), cdiv(nproj, 32), nz2), (32, 32, 1), [tmp_p, datac, i32(n), i32(nproj), i32(nz2)])
+    datac = torch.fft.fft(datac, dim=-1).contiguous()
+    m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
+    mod.launch("c1dfftshift", (cdiv(n, 32), cdiv(nproj, 32), nz2), (32, 32, 1),
+               [datac, np.float32(4 / n), i32(n), i32(nproj), i32(nz2)])
+    prune = "gather_kernel_center_prune_naive" if use_naive_prune else "gather_kernel_center_angle_based_prune"
+    mod.launch(prune, (cdiv(center_size, 256), center_size, 1), (256, 1, 1),
+               [angle_range, i32(pi_count * 2 + 1), sth, i32(m), i32(center_size), i32(n), i32(nproj)])
+    mod.launch("gather_kernel_center", (cdiv(center_size, 32), cdiv(center_size, 4), nz2), (32, 4, 1),
+               [datac, fde, angle_range, i32(pi_count * 2 + 1), theta, sidx.to(torch.int64).contiguous(), i32(m),
+                np.float32(mu), i32(center_size), i32(n), i32(nproj), i32(nz2)])
+    mod.launch("c2dfftshift", (cdiv(2 * n, 32), cdiv(2 * n, 8), nz2), (32, 8, 1), [fde, i32(n), i32(nz2)])
+    for z in range(nz2):
+        fde[z] = torch.fft.ifft2(fde[z])
+    mod.launch("c2dfftshift", (cdiv(2 * n, 32), cdiv(2 * n, 8), nz2), (32, 8, 1), [fde, i32(n), i32(nz2)])
+    odd_r = bool(recon_size % 2)
+    unpad_z = nz - odd_v
+    um = (n - odd_h) // 2 - recon_size // 2
+    up = (n - odd_h) // 2 + (recon_size + odd_r) // 2
+    rs = up - um
+    recon = torch.empty((unpad_z, rs, rs), dtype=torch.float32, device=dev)
+    mod.launch("unpadding_mul_phi", (cdiv(rs, 32), cdiv(rs, 32), nz2), (32, 32, 1),
+               [recon, fde, np.float32(mu), i32(nproj), i32(up), i32(unpad_z), i32(um), i32(n), i32(nz2)])
+    torch.cuda.synchronize()
+    return recon

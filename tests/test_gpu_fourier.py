@@ -1,0 +1,89 @@
+"""FOURIER_INV: the reference's pinned goldens, z-block invariance, odd/even shape matrix
+(reference tests/test_RecToolsDIRCuPy.py:225-468) and kernel-level parity with the reference's
+own fft_us_kernels.cu kernels run from oracle/_ref."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+from numpy.testing import assert_allclose
+
+import ref_kernels as R
+from conftest import rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+LABELS = ["angles", "detY", "detX"]
+
+
+def _dir(angles, detX, detY, obj=None, pad=0):
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+
+    return RecToolsDIRCuPy(DetectorsDimH=detX, DetectorsDimH_pad=pad, DetectorsDimV=detY, CenterRotOffset=0.0,
+                           AnglesVec=angles, ObjSize=detX if obj is None else obj, device_projector=0)
+
+
+def test_fourier_inv_golden(scan):  # tests/test_RecToolsDIRCuPy.py:225-250
+    data, angles = scan
+    rec = _dir(angles, 160, 128).FOURIER_INV(torch.from_numpy(data).cuda(), data_axes_labels_order=LABELS,
+                                             recon_mask_radius=2.0).cpu().numpy()
+    assert_allclose(rec.min(), -0.0372409, atol=1e-5)
+    assert_allclose(rec.max(), 0.1035610, atol=1e-4)
+    assert rec.dtype == np.float32 and rec.shape == (128, 160, 160)
+
+
+@pytest.mark.parametrize("blocks", [2, 8, 32])
+def test_fourier_inv_vert_blocks(scan, blocks):  # :253-288
+    data, angles = scan
+    d = torch.from_numpy(data).cuda()
+    R_ = _dir(angles, 160, blocks)
+    out = torch.empty((128, 160, 160), device="cuda")
+    for s in range(0, 128, blocks):
+        out[s:s + blocks] = R_.FOURIER_INV(d[:, s:s + blocks, :], recon_mask_radius=2.0, data_axes_labels_order=LABELS)
+    rec = out.cpu().numpy()
+    assert_allclose(rec.min(), -0.0372409, atol=1e-5)
+    assert_allclose(rec.max(), 0.1035610, atol=1e-4)
+
+
+def test_fourier_inv_last_block_odd(scan):  # :291-337
+    data, angles = scan
+    d = torch.from_numpy(data).cuda()
+    a = _dir(angles, 160, 125).FOURIER_INV(d[:, :125, :], recon_mask_radius=2.0, data_axes_labels_order=LABELS)
+    b = _dir(angles, 160, 3).FOURIER_INV(d[:, 125:, :], recon_mask_radius=2.0, data_axes_labels_order=LABELS)
+    rec = torch.cat((a, b)).cpu().numpy()
+    assert rec.shape == (128, 160, 160)
+    assert_allclose(rec.min(), -0.0372409, atol=1e-5)
+    assert_allclose(rec.max(), 0.1035610, atol=1e-4)
+
+
+@pytest.mark.parametrize("detX,obj", [(341, 340), (342, 341), (342, 342), (341, 341)])
+def test_fourier_inv_odd_even_shapes(detX, obj):  # :340-440 (sizes reduced 4x)
+    rng = np.random.default_rng(0)
+    data = rng.integers(7515, 37624, size=(225, 3, detX)).astype(np.float32)
+    angles = np.linspace(0, math.pi, data.shape[0])
+    rec = _dir(angles, detX, 3, obj).FOURIER_INV(torch.from_numpy(data).cuda(), data_axes_labels_order=LABELS)
+    assert rec.dtype == torch.float32 and tuple(rec.shape) == (3, obj, obj)
+    assert torch.isfinite(rec).all()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref cubins not built")
+@pytest.mark.parametrize("case", [(16, 180, 160, 160, 0), (6, 120, 97, 96, 0), (5, 90, 130, 100, 3), (4, 400, 256, 256, 0)])
+def test_fourier_inv_vs_reference_kernels(scan, case):
+    nz, na, detX, obj, pad = case
+    data, angles_scan = scan
+    if (na, detX) == (180, 160):
+        d = torch.from_numpy(np.ascontiguousarray(np.swapaxes(data[:, 40:40 + nz, :], 0, 1))).cuda()
+        angles = angles_scan
+    else:
+        g = torch.Generator(device="cuda").manual_seed(na)
+        d = torch.rand((nz, na, detX), device="cuda", generator=g)
+        angles = np.linspace(0, math.pi, na, endpoint=False).astype(np.float32)
+        if na == 400:
+            angles = np.linspace(0, 2 * math.pi, na, endpoint=False).astype(np.float32)  # 360-degree scan
+    ref = R.ref_FOURIER_INV(d, angles, obj, 0.0, pad).cpu().numpy()
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+
+    got = RecToolsDIRCuPy(detX, pad, nz, 0.0, angles, obj, device_projector=0).FOURIER_INV(d).cpu().numpy()
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)
+    assert rel_max(got, ref) < 1e-4, rel_max(got, ref)

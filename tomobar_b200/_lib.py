@@ -45,6 +45,11 @@ SIGNATURES = {
     "tmb_sinc_filter": (_i, [_f, _fp, _i, _f, _vp]),
     "tmb_apply_filter": (_i, [_fp, _fp, _sz, _i, _vp]),
     "tmb_circular_mask": (_i, [_fp, _i, _i, _f, _vp]),
+    "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),
+    "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
+    "tmb_fi_gather": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _vp]),
+    "tmb_fi_sign2d": (_i, [_fp, _i, _i, _vp]),
+    "tmb_fi_unpad": (_i, [_fp, _fp, _f, _i, _i, _i, _i, _i, _i, _vp]),
     "tmb_fp3d_host": (_i, [_vp, _i, _fp, _fp]),
     "tmb_bp3d_host": (_i, [_vp, _i, _fp, _fp]),
 }

@@ -1,0 +1,250 @@
+// FOURIER_INV (USFFT gridding reconstruction) kernels for sm_100a.
+//
+// Replaces the default ("centre gather") path of RecToolsDIRCuPy.FOURIER_INV
+// (methodsDIR_CuPy.py:152-447) whose kernels live in cuda_kernels/fft_us_kernels.cu:
+//   r2c_c1dfftshift (:529-557)  -> k_fi_pack
+//   c1dfftshift     (:559-586)  -> k_fi_scale_sign
+//   gather_kernel_center_angle_based_prune (:193-319) + gather_kernel_center (:468-527)
+//                               -> k_fi_gather (angle ranges found on the fly, no uint16 table)
+//   c2dfftshift     (:588-609)  -> k_fi_sign2d
+//   unpadding_mul_phi (:611-657)-> k_fi_unpad
+// The FFTs themselves run in cuFFT (called by the host through torch.fft).
+//
+// k_fi_gather: one thread owns one point of the 2n x 2n Cartesian frequency grid and a chunk of
+// complex slices.  A polar line (projection) contributes to the point when it passes within
+// r = sqrt(2)(m + 1/2)/(2n) of it, i.e. when its angle lies in phi +- asin(r/|p|) (mod pi); the
+// thread finds those index ranges in the sorted angle list by binary search, then, per line,
+// walks the chord inside the disc and accumulates Gaussian-weighted samples.  The Gaussian
+// weight is computed once per sample and applied to every slice of the chunk (the reference
+// launches one thread per (point, slice) and recomputes it for each slice).
+#include "tmb_common.h"
+
+namespace tmb {
+
+constexpr float FI_PI = 3.14159265358979323846f;
+constexpr int FI_SC = 4;  // complex slices per thread in the gather
+
+__global__ void k_fi_pack(const float *__restrict__ in, float2 *__restrict__ out, int n, int nproj, int nz2) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+  const int tz = blockIdx.z;
+  if (tx >= n || ty >= nproj || tz >= nz2) return;
+  const size_t plane = (size_t)n * nproj;
+  const size_t i = (size_t)ty * n + tx;
+  const float sgn = (tx & 1) ? 1.f : -1.f;
+  // slices 2t and 2t+1 become the real and imaginary part of complex slice t
+  out[tz * plane + i] = make_float2(in[(2 * (size_t)tz) * plane + i] * sgn, in[(2 * (size_t)tz + 1) * plane + i] * sgn);
+}
+
+__global__ void k_fi_scale_sign(float2 *__restrict__ d, float c, int n, size_t rows) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tx >= n) return;
+  const float sgn = (tx & 1) ? 1.f : -1.f;
+  for (size_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    float2 v = d[r * n + tx];
+    if (c == 1.f) {
+      v.x = v.x * sgn;
+      v.y = v.y * sgn;
+    } else {
+      v.x = v.x * c * sgn;
+      v.y = v.y * c * sgn;
+    }
+    d[r * n + tx] = v;
+  }
+}
+
+__global__ void k_fi_sign2d(float2 *__restrict__ f, int n2, int nz2) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+  if (tx >= n2 || ty >= n2) return;
+  if (((tx ^ ty) & 1) == 0) return;  // sign +1
+  for (int z = blockIdx.z; z < nz2; z += gridDim.z) {
+    float2 *p = f + (size_t)z * n2 * n2 + (size_t)ty * n2 + tx;
+    float2 v = *p;
+    v.x = -v.x;
+    v.y = -v.y;
+    *p = v;
+  }
+}
+
+__device__ __forceinline__ int lower_bound_f(const float *__restrict__ a, int n, float v) {
+  int lo = 0, hi = n;  // first index with a[i] >= v
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound_f(const float *__restrict__ a, int n, float v) {
+  int lo = 0, hi = n;  // first index with a[i] > v
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// contribution of polar line `proj` to the grid point (fft_us_kernels.cu:379-466)
+__device__ __forceinline__ void fi_line(const float2 *__restrict__ g, float theta, float2 (&acc)[FI_SC], float px,
+                                        float py, float radius_2, int proj, int z0, int nzc, float coeff0,
+                                        float coeff1, int n, int nproj) {
+  float st, ct;
+  __sincosf(theta, &st, &ct);
+  const float pr = 0.5f, pr2 = 0.25f;
+  const float vx = pr * ct, vy = pr * st;
+  const float dot = vx * px + vy * py;
+  const float mx = dot * vx / pr2, my = dot * vy / pr2;
+  const float d2 = (mx - px) * (mx - px) + (my - py) * (my - py);
+  if (!(radius_2 >= d2)) return;
+  const float reach = __fsqrt_rn(radius_2 - d2);
+  int rmin, rmax;
+  if (fabsf(vx) > fabsf(vy)) {
+    rmin = n / 2 - 1 + (int)floorf((mx - reach * vx / pr) / (2.f * vx / n));
+    rmax = n / 2 + 1 + (int)floorf((mx + reach * vx / pr) / (2.f * vx / n));
+  } else {
+    rmin = n / 2 - 1 + (int)floorf((my - reach * vy / pr) / (2.f * vy / n));
+    rmax = n / 2 + 1 + (int)floorf((my + reach * vy / pr) / (2.f * vy / n));
+  }
+  if (rmin > rmax) { const int t = rmax; rmax = rmin; rmin = t; }
+  rmin = min(max(rmin, 0), n - 1);
+  rmax = min(max(rmax, 0), n - 1);
+  const size_t plane = (size_t)n * nproj;
+  const float2 *row = g + (size_t)proj * n + (size_t)z0 * plane;
+  for (int ri = rmin; ri < rmax; ++ri) {  // exclusive upper bound, like the reference
+    float x0 = (ri - n / 2) / (float)n * ct;
+    float y0 = (ri - n / 2) / (float)n * st;
+    if (x0 >= 0.5f) x0 = 0.5f - 1e-5;
+    if (y0 >= 0.5f) y0 = 0.5f - 1e-5;
+    const float w0 = px - x0, w1 = py - y0;
+    const float w = coeff0 * __expf(coeff1 * (w0 * w0 + w1 * w1));
+#pragma unroll
+    for (int s = 0; s < FI_SC; ++s) {
+      if (s < nzc) {
+        const float2 v = __ldg(row + (size_t)s * plane + ri);
+        acc[s].x += v.x * w;
+        acc[s].y += v.y * w;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_fi_gather(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta,
+                const float *__restrict__ sth, const int *__restrict__ sidx, int m, float mu, int n, int nproj,
+                int nz2) {
+  const int n2 = 2 * n;
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z0 = blockIdx.z * FI_SC;
+  if (tx >= n2 || ty >= n2) return;
+  const int nzc = min(FI_SC, nz2 - z0);
+  const float coeff0 = FI_PI / mu;
+  const float coeff1 = -FI_PI * FI_PI / mu;
+  const int fs2 = n2 * n2;
+  const float radius_2 = 2.f * ((float)m + 0.5f) * ((float)m + 0.5f) / fs2;
+  const float px = (float)(tx - n) / (float)n2, py = (float)(n - ty) / (float)n2;
+  const float len2 = px * px + py * py;
+
+  float2 acc[FI_SC];
+#pragma unroll
+  for (int s = 0; s < FI_SC; ++s) acc[s] = make_float2(0.f, 0.f);
+
+  if (radius_2 >= len2) {
+    for (int j = 0; j < nproj; ++j) {
+      const int proj = __ldg(sidx + j);
+      fi_line(g, __ldg(theta + proj), acc, px, py, radius_2, proj, z0, nzc, coeff0, coeff1, n, nproj);
+    }
+  } else {
+    // angles whose line passes within the disc: phi +- delta (mod pi); a small slack keeps the
+    // range a superset, fi_line applies the exact test
+    const float len = __fsqrt_rn(len2);
+    const float delta = asinf(fminf(1.f, __fsqrt_rn(radius_2) / len)) + 2e-3f;
+    const float phi = atan2f(py, px);
+    const float tmin = __ldg(sth), tmax = __ldg(sth + nproj - 1);
+    const int kmin = (int)ceilf((tmin - phi - delta) / FI_PI);
+    const int kmax = (int)floorf((tmax - phi + delta) / FI_PI);
+    int done = 0;  // first sorted index not yet consumed (ranges may touch near the centre)
+    for (int k = kmin; k <= kmax; ++k) {
+      const float a = phi - delta + k * FI_PI, b = phi + delta + k * FI_PI;
+      int lo = lower_bound_f(sth, nproj, a);
+      const int hi = upper_bound_f(sth, nproj, b);
+      lo = max(lo, done);
+      for (int j = lo; j < hi; ++j) {
+        const int proj = __ldg(sidx + j);
+        fi_line(g, __ldg(theta + proj), acc, px, py, radius_2, proj, z0, nzc, coeff0, coeff1, n, nproj);
+      }
+      done = max(done, hi);
+    }
+  }
+  const size_t o = (size_t)ty * n2 + tx;
+#pragma unroll
+  for (int s = 0; s < FI_SC; ++s)
+    if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = acc[s];
+}
+
+__global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__ f, float mu, int nproj, int up,
+                           int unpad_z, int um, int n, int nz2) {
+  const int rxu = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ryu = blockIdx.y * blockDim.y + threadIdx.y;
+  const int rz = blockIdx.z;
+  const int rx = um + rxu, ry = um + ryu;
+  if (rx >= up || ry >= up || rz >= nz2) return;
+  const int n2 = 2 * n;
+  const int rs = up - um;
+  const size_t rs2 = (size_t)rs * rs;
+  const float2 v = f[(size_t)rz * n2 * n2 + (size_t)(n / 2 + ry) * n2 + (n / 2 + rx)];
+  const float ddx = -0.5f + rx * 1.f / n;
+  const float ddy = -0.5f + ry * 1.f / n;
+  const float phi = expf(mu * (n * n) * (ddx * ddx + ddy * ddy)) * ((float)(1 - n % 4) / nproj);
+  const size_t ri = (size_t)ryu * rs + rxu;
+  // complex slice t carries output slices 2t (real) and 2t+1 (imaginary)
+  recon[(size_t)rz * 2 * rs2 + ri] = v.x * phi;
+  if (2 * rz + 1 < unpad_z) recon[((size_t)rz * 2 + 1) * rs2 + ri] = v.y * phi;
+}
+
+}  // namespace tmb
+
+using namespace tmb;
+
+extern "C" int tmb_fi_pack(const float *in, float *datac, int n, int nproj, int nz2, void *stream) {
+  TMB_REQUIRE(in && datac && n > 0 && nproj > 0 && nz2 > 0, "tmb_fi_pack: bad argument");
+  dim3 block(32, 8), grid((n + 31) / 32, (nproj + 7) / 8, nz2);
+  k_fi_pack<<<grid, block, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float2 *>(datac), n, nproj, nz2);
+  return check_launch("k_fi_pack");
+}
+
+extern "C" int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream) {
+  TMB_REQUIRE(datac && n > 0 && nproj > 0 && nz2 > 0, "tmb_fi_scale_sign: bad argument");
+  const size_t rows = (size_t)nproj * nz2;
+  dim3 grid((n + 127) / 128, (unsigned)(rows < 4096 ? rows : 4096));
+  k_fi_scale_sign<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(datac), c, n, rows);
+  return check_launch("k_fi_scale_sign");
+}
+
+extern "C" int tmb_fi_gather(const float *datac, float *fde, const float *theta, const float *sorted_theta,
+                             const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream) {
+  TMB_REQUIRE(datac && fde && theta && sorted_theta && sorted_idx, "tmb_fi_gather: null argument");
+  TMB_REQUIRE(n > 0 && nproj > 0 && nz2 > 0 && m > 0 && mu > 0.f, "tmb_fi_gather: bad argument");
+  dim3 block(32, 4), grid((2 * n + 31) / 32, (2 * n + 3) / 4, (nz2 + FI_SC - 1) / FI_SC);
+  k_fi_gather<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
+                                                        reinterpret_cast<float2 *>(fde), theta, sorted_theta,
+                                                        sorted_idx, m, mu, n, nproj, nz2);
+  return check_launch("k_fi_gather");
+}
+
+extern "C" int tmb_fi_sign2d(float *fde, int n, int nz2, void *stream) {
+  TMB_REQUIRE(fde && n > 0 && nz2 > 0, "tmb_fi_sign2d: bad argument");
+  dim3 block(32, 8), grid((2 * n + 31) / 32, (2 * n + 7) / 8, nz2 < 64 ? nz2 : 64);
+  k_fi_sign2d<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(fde), 2 * n, nz2);
+  return check_launch("k_fi_sign2d");
+}
+
+extern "C" int tmb_fi_unpad(float *recon, const float *fde, float mu, int nproj, int unpad_recon_p, int unpad_z,
+                            int unpad_recon_m, int n, int nz2, void *stream) {
+  TMB_REQUIRE(recon && fde && n > 0 && nz2 > 0 && unpad_recon_p > unpad_recon_m, "tmb_fi_unpad: bad argument");
+  const int rs = unpad_recon_p - unpad_recon_m;
+  dim3 block(32, 8), grid((rs + 31) / 32, (rs + 7) / 8, nz2);
+  k_fi_unpad<<<grid, block, 0, (cudaStream_t)stream>>>(recon, reinterpret_cast<const float2 *>(fde), mu, nproj,
+                                                       unpad_recon_p, unpad_z, unpad_recon_m, n, nz2);
+  return check_launch("k_fi_unpad");
+}

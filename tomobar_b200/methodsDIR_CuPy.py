@@ -1,18 +1,20 @@
 """Direct reconstruction on B200 behind the ``RecToolsDIRCuPy`` interface
-(tomobar/methodsDIR_CuPy.py:26-150): FORWPROJ, BACKPROJ, FBP.  Arrays are float32 CUDA torch
-tensors.  FOURIER_INV is provided by ``tomobar_b200.fourier_inv`` when built."""
+(tomobar/methodsDIR_CuPy.py:26-447): FORWPROJ, BACKPROJ, FBP, FOURIER_INV.  Arrays are float32
+CUDA torch tensors."""
 
 from __future__ import annotations
 
+import math
 from typing import Literal
 
 import numpy as np
 import torch
 
-from tomobar_b200._tensors import as_cuda_f32
-from tomobar_b200.fourier import _filtersinc3D_cupy
+from tomobar_b200._lib import lib, check
+from tomobar_b200._tensors import as_cuda_f32, ptr, stream_ptr
+from tomobar_b200.fourier import _filtersinc3D_cupy, calc_filter
 from tomobar_b200.projector import ProjTools3D
-from tomobar_b200.supp.funcs import _data_dims_swapper
+from tomobar_b200.supp.funcs import _data_dims_swapper, _parse_device_argument
 from tomobar_b200.supp.suppTools import _apply_horiz_detector_padding, check_kwargs
 
 
@@ -51,20 +53,16 @@ class RecToolsDIRCuPy:
         self.projector = projector
         if DetectorsDimV == 0 or DetectorsDimV is None:
             DetectorsDimV = 1
-        if DetectorsDimH_pad > 0:
-            # padded detector => padded reconstruction grid, like methodsDIR.py's parent class
-            obj = ObjSize
-        else:
-            obj = ObjSize
+        arch, gpu_index = _parse_device_argument(device_projector)
         self.Atools = ProjTools3D(
             DetectorsDimH,
             DetectorsDimH_pad,
             DetectorsDimV,
             AnglesVec,
             CenterRotOffset,
-            obj,
-            "gpu",
-            device_projector if isinstance(device_projector, int) else 0,
+            ObjSize,
+            arch,
+            gpu_index,
             None,
             quantise_weights=quantise_weights,
         )
@@ -103,3 +101,157 @@ class RecToolsDIRCuPy:
         data = data.swapaxes(0, 1).contiguous()
         reconstruction = self.Atools._backprojCuPy(data)
         return check_kwargs(reconstruction, **kwargs)
+
+    # ------------------------------------------------------------------------------------------
+    _FILTERS = ("none", "ramp", "shepp", "cosine", "cosine2", "hamming", "hann", "parzen")
+
+    def FOURIER_INV(self, data, **kwargs) -> torch.Tensor:
+        """Direct Fourier inversion on unequally spaced grids (USFFT gridding, Nikitin's
+        "fourierrec"; methodsDIR_CuPy.py:152-447, default centre-gather path).
+
+        Keyword Args:
+            data_axes_labels_order (list, None): axes of the input; default ["detY", "angles", "detX"].
+            recon_mask_radius (float): circular mask radius.
+            filter_type (str): none, ramp, shepp, cosine, cosine2, hamming, hann, parzen.
+            cutoff_freq (float): filter cutoff (default 1.0).
+            padding (int): extra zero padding of the frequency grid.
+            power_of_2_oversampling / power_of_2_cropping (bool): as in the reference.
+        The memory-tuning keywords of the reference (chunk_count, min_mem_usage_*, block_dim*) are
+        accepted and ignored; ``center_size`` smaller than the full grid (the scatter kernels) is
+        not built.
+        """
+        kwargs.update({"cupyrun": True})
+        cutoff_freq = 1.0
+        filter_type = "shepp"
+        oversampling_level = 4
+        power_of_2_oversampling = True
+        power_of_2_cropping = False
+        padding = 0
+        data = as_cuda_f32(data, self.Atools.device, "projection data")
+        for key, value in kwargs.items():
+            if value is None:
+                continue
+            if key == "data_axes_labels_order":
+                data = _data_dims_swapper(data, value, ["detY", "angles", "detX"])
+            elif key == "center_size":
+                if value < 2 * (data.shape[-1] + 2 * self.detectors_x_pad):
+                    raise NotImplementedError("FOURIER_INV: only the full-grid centre gather is built")
+            elif key == "cutoff_freq":
+                cutoff_freq = value
+            elif key == "filter_type":
+                if value not in self._FILTERS:
+                    print("Unknown filter name, please use: none, ramp, shepp, cosine, cosine2, hamming, hann or "
+                          "parzen. Set to shepp filter")
+                else:
+                    filter_type = value
+            elif key == "power_of_2_oversampling":
+                power_of_2_oversampling = value
+            elif key == "power_of_2_cropping":
+                power_of_2_cropping = value
+            elif key == "padding":
+                if not isinstance(value, int) or value < 0:
+                    print(f"Invalid padding: {value}. Set to 0")
+                else:
+                    padding = value
+
+        dev = data.device
+        nz, nproj, data_n = data.shape
+        recon_size = self.recon_size
+        if recon_size > data_n:
+            raise ValueError(
+                "The reconstruction size {} should not be larger than the size of the horizontal detector {}".format(
+                    recon_size, data_n
+                )
+            )
+        # odd sizes are padded to even: slices are processed in pairs (:268-282)
+        odd_horiz, odd_vert = bool(data_n % 2), bool(nz % 2)
+        data_n += odd_horiz
+        nz += odd_vert
+        if odd_horiz or odd_vert:
+            data_p = torch.zeros((nz, nproj, data_n), dtype=torch.float32, device=dev)
+            data_p[: nz - odd_vert, :, : data_n - odd_horiz] = data
+            if odd_horiz:
+                data_p[: nz - odd_vert, :, -1] = data[..., -1]
+            data = data_p
+        data = data.contiguous()
+
+        n = data_n + self.detectors_x_pad * 2 + padding * 2
+        if power_of_2_cropping:
+            n_pow2 = 2 ** math.ceil(math.log2(n))
+            if 0.9 < n / n_pow2:
+                n = n_pow2
+        nz2 = nz // 2
+
+        theta = torch.as_tensor(-np.asarray(self.angles_vec), dtype=torch.float32, device=dev)
+        sorted_theta, sorted_idx = torch.sort(theta)
+        sorted_idx = sorted_idx.to(torch.int32)
+
+        eps = 1e-4  # accuracy of the USFFT
+        mu = -np.log(eps) / (2 * n * n)
+        st = torch.cuda.current_stream(dev).cuda_stream
+
+        with torch.cuda.device(dev):
+            # STEP 0: filtering on an oversampled detector with a half-pixel phase ramp (:449-545)
+            tmp_p = self._fourier_filter(data, data_n, n, power_of_2_oversampling, oversampling_level,
+                                         filter_type, cutoff_freq)
+            del data
+            # STEP 1: pair slices into complex slices, 1-D FFT along the detector (:645-683, :725-754)
+            datac = torch.empty((nz2, nproj, n), dtype=torch.complex64, device=dev)
+            check(lib.tmb_fi_pack(ptr(tmp_p), ptr(datac), n, nproj, nz2, st), "tmb_fi_pack")
+            del tmp_p
+            datac = torch.fft.fft(datac, dim=-1)
+            check(lib.tmb_fi_scale_sign(ptr(datac), float(np.float32(4 / n)), n, nproj, nz2, st), "tmb_fi_scale_sign")
+            m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
+            # STEP 2: gather polar samples onto the 2n x 2n Cartesian grid (:781-816)
+            fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+            check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
+                                    float(np.float32(mu)), n, nproj, nz2, st), "tmb_fi_gather")
+            del datac
+            # STEP 3: centred 2-D inverse FFT (:851-896)
+            check(lib.tmb_fi_sign2d(ptr(fde), n, nz2, st), "tmb_fi_sign2d")
+            chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))  # bound cuFFT workspace
+            for s0 in range(0, nz2, chunk):
+                fde[s0:s0 + chunk] = torch.fft.ifft2(fde[s0:s0 + chunk], dim=(-2, -1))
+            check(lib.tmb_fi_sign2d(ptr(fde), n, nz2, st), "tmb_fi_sign2d")
+            # STEP 4: crop, de-apodise, unpack the slice pairs (:920-966)
+            odd_recon = bool(recon_size % 2)
+            unpad_z = nz - odd_vert
+            um = (n - odd_horiz) // 2 - recon_size // 2
+            up = (n - odd_horiz) // 2 + (recon_size + odd_recon) // 2
+            rs = up - um
+            recon_up = torch.empty((unpad_z, rs, rs), dtype=torch.float32, device=dev)
+            check(lib.tmb_fi_unpad(ptr(recon_up), ptr(fde), float(np.float32(mu)), nproj, up, unpad_z, um, n, nz2, st),
+                  "tmb_fi_unpad")
+            del fde
+        return check_kwargs(recon_up, **kwargs)
+
+    def _fourier_filter(self, data, raw_width, width, power_of_2_oversampling, oversampling_level, filter_type,
+                        cutoff_freq) -> torch.Tensor:
+        """rfft -> analytic filter with the rotation-axis phase ramp -> irfft on an edge-padded,
+        oversampled detector; cropped to ``width`` (methodsDIR_CuPy.py:449-545)."""
+        if power_of_2_oversampling:
+            over = 2 ** math.ceil(math.log2(raw_width * 3))
+            if width > over:
+                over = 2 ** math.ceil(math.log2(width))
+        else:
+            over = max(int(oversampling_level * raw_width), width)
+        padding_m = over // 2 - raw_width // 2
+        unpad_m = over // 2 - width // 2
+        unpad_p = over // 2 + width // 2
+        rotation_axis = self.centre_of_rotation + 0.5
+        dev = data.device
+        wfilter = torch.as_tensor(calc_filter(over, filter_type, cutoff_freq), device=dev)
+        t = torch.fft.rfftfreq(over, device=dev).to(torch.float32)
+        w = wfilter * torch.exp((-2 * np.pi * 1j * rotation_axis) * t.to(torch.complex64))
+        nz, nproj, _ = data.shape
+        out = torch.empty((nz, nproj, width), dtype=torch.float32, device=dev)
+        # slice chunks bound the oversampled temporaries (the reference chunks for the same reason)
+        per = max(1, (1 << 27) // (nproj * over))
+        for z0 in range(0, nz, per):
+            blk = data[z0:z0 + per]
+            left = blk[..., :1].expand(-1, -1, padding_m)
+            right = blk[..., -1:].expand(-1, -1, padding_m)
+            tmp = torch.cat((left, blk, right), dim=-1)
+            tmp = torch.fft.irfft(w * torch.fft.rfft(tmp, dim=2), n=over, dim=2)
+            out[z0:z0 + per] = tmp[:, :, unpad_m:unpad_p]
+        return out
