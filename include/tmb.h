@@ -92,8 +92,22 @@ int tmb_rof_tv(const float *in, float *out, int dz, int dy, int dx, float regula
                int iterations, float time_marching_parameter, int half_precision, void *workspace,
                void *stream);
 
+/* One Chambolle-Pock iteration on caller-owned ping-pong buffers: the kernel-level seam of
+ * regularisersCuPy.py:255-292 (one launch per inner iteration).  p*_in / p*_out are fp32, or fp16
+ * when half_precision.  For a z-SHARD of a larger volume set ghost_lo / ghost_hi: with ghost_hi
+ * plane dz of u_in must exist (the next shard's first plane); with ghost_lo plane -1 of u_in and of
+ * p1_in..p3_in must exist (the previous shard's last plane).  The caller refreshes those ghost planes
+ * between iterations; the sharded result is then bit-identical to the whole-volume one.
+ * Ghost planes need dx % 4 == 0 and 16-byte aligned arrays (TMB_ERR_UNSUPPORTED otherwise).       */
+int tmb_pd_tv_iter(const float *in, const float *u_in, float *u_out, const void *p1_in, const void *p2_in,
+                   const void *p3_in, void *p1_out, void *p2_out, void *p3_out, int dz, int dy, int dx,
+                   float regularisation_parameter, int methodTV, int nonneg, float lipschitz_const,
+                   int half_precision, int ghost_lo, int ghost_hi, void *stream);
+
 /* Debug/test switch: 1 routes 3-D TV through the simple one-thread-per-voxel kernels instead of
- * the z-marching ones (same arithmetic; used by the parity tests).  Returns the old value. */
+ * the z-marching ones, 2 through the CTA-tiled z-marching kernels, 3 through the register-fed
+ * warp-strip kernels instead of the TMA-fed ones (same arithmetic; used by the parity tests).
+ * Returns the old value. */
 int tmb_tv_set_simple_kernels(int enable);
 
 /* ---- fused elementwise steps of the iterative loops ---------------------------------------
@@ -121,6 +135,12 @@ int tmb_sinc_filter(float cutoff, float *f, int n, float multiplier, void *strea
 int tmb_apply_filter(float *spec, const float *f, size_t rows, int nbins, void *stream);
 /* circular mask (supp/suppTools.py:364-396), in place on vol[nz][n][n]                        */
 int tmb_circular_mask(float *vol, int nz, int n, float radius, void *stream);
+
+/* flat / dark-field normalisation with negative log (supp/suppTools.py:187-264, methods "mean" /
+ * "median": the caller averages the flats / darks): data[n0][n1][n2] raw projections (uint16 when
+ * data_is_u16, else fp32) with the angle axis 0 or 1; flat_mean / dark_mean [.][n2]; out fp32.     */
+int tmb_normalise(const void *data, int data_is_u16, const float *flat_mean, const float *dark_mean,
+                  float *out, int n0, int n1, int n2, int angle_axis, int take_log, void *stream);
 
 /* ---- FOURIER_INV (USFFT gridding) kernels ----------------------------------------------------
  * Replace the default centre-gather path of RecToolsDIRCuPy.FOURIER_INV (methodsDIR_CuPy.py:152-447)

@@ -18,7 +18,7 @@ def _vol(shape, seed=0):
     return v * np.float32(0.02)
 
 
-@pytest.mark.parametrize("shape", [(12, 33, 47), (1, 40, 52), (40, 52), (5, 1, 64), (3, 130, 129)])
+@pytest.mark.parametrize("shape", [(12, 33, 47), (1, 40, 52), (40, 52), (5, 1, 64), (3, 130, 129), (6, 19, 136), (2, 2, 4)])
 @pytest.mark.parametrize("methodTV", [0, 1])
 @pytest.mark.parametrize("nonneg", [0, 1])
 @pytest.mark.parametrize("half", [False, True])
@@ -66,22 +66,25 @@ def test_tv_errors_and_edge_cases():
     assert torch.equal(x, x0) and not torch.equal(a, b)
 
 
-@pytest.mark.parametrize("shape", [(70, 100, 150), (33, 9, 65), (64, 64, 64)])
+@pytest.mark.parametrize("shape", [(70, 100, 150), (33, 9, 65), (64, 64, 64), (97, 35, 260), (130, 5, 128), (40, 64, 8)])
 @pytest.mark.parametrize("half", [False, True])
 def test_marching_kernels_match_simple_kernels(shape, half):
-    """The z-marching 3-D kernels and the one-thread-per-voxel kernels share their arithmetic."""
+    """The warp-strip kernels (dx % 4 == 0; TMA-fed = mode 0, register-fed = mode 3), the CTA-tiled
+    z-marching kernels (mode 2) and the one-thread-per-voxel kernels (mode 1) share their arithmetic."""
     from tomobar_b200._lib import lib
     from tomobar_b200.regularisersCuPy import PD_TV_cupy, ROF_TV_cupy
 
     v = torch.from_numpy(_vol(shape, 7)).cuda()
-    a = PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half)
-    r = ROF_TV_cupy(v, 3e-4, 9, 1e-3, 0, half)
-    old = lib.tmb_tv_set_simple_kernels(1)
-    try:
-        b = PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half)
-        q = ROF_TV_cupy(v, 3e-4, 9, 1e-3, 0, half)
-    finally:
-        lib.tmb_tv_set_simple_kernels(old)
+    res = {}
+    for mode in (0, 1, 2, 3):
+        old = lib.tmb_tv_set_simple_kernels(mode)
+        try:
+            res[mode] = (PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half).cpu().numpy(),
+                         PD_TV_cupy(v, 5e-4, 4, 1, 0, 12.0, 0, half).cpu().numpy(),
+                         ROF_TV_cupy(v, 3e-4, 9, 1e-3, 0, half).cpu().numpy())
+        finally:
+            lib.tmb_tv_set_simple_kernels(old)
     tol = 2e-3 if half else 2e-6
-    assert rel_max(a.cpu().numpy(), b.cpu().numpy()) < tol
-    assert rel_max(r.cpu().numpy(), q.cpu().numpy()) < tol
+    for mode in (0, 2, 3):
+        for a, b in zip(res[mode], res[1]):
+            assert rel_max(a, b) < tol

@@ -1,0 +1,79 @@
+"""z-sharded 3-D PD_TV on ONE GPU: the volume is cut into z-blocks that are advanced in lock step
+through ``tmb_pd_tv_iter`` with their ghost planes refreshed by plain copies between the inner
+iterations (what ``ShardedPDTV`` does with point-to-point messages).  The assembled result must be
+bit-identical to the whole-volume prox.  (The multi-process version: tests/test_gpu_multi.py.)"""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _vol(shape, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    v = torch.randn(shape, device="cuda", generator=g) * 0.01
+    v += (torch.rand(shape, device="cuda", generator=g) > 0.5).float() * 0.02
+    return v
+
+
+def _sharded_prox(v, cuts, lam, iters, methodTV, nonneg, lip, half):
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr, stream_ptr
+
+    nz, ny, nx = v.shape
+    bounds = list(zip([0] + cuts, cuts + [nz]))
+    pdt = torch.float16 if half else torch.float32
+    S = []
+    for (z0, z1) in bounds:
+        nzl = z1 - z0
+        U = [torch.zeros((nzl + 2, ny, nx), device="cuda") for _ in range(2)]
+        P = [[torch.zeros((nzl + 1, ny, nx), dtype=pdt, device="cuda") for _ in range(3)] for _ in range(2)]
+        U[0][1:nzl + 1] = v[z0:z1]
+        S.append(dict(nzl=nzl, U=U, P=P, data=v[z0:z1].contiguous()))
+    for it in range(iters):
+        a, b = it % 2, 1 - it % 2
+        for i, s in enumerate(S):  # halo refresh (ShardedPDTV.exchange)
+            if i + 1 < len(S):
+                nxt = S[i + 1]
+                nxt["U"][a][0].copy_(s["U"][a][s["nzl"]])
+                for c in range(3):
+                    nxt["P"][a][c][0].copy_(s["P"][a][c][s["nzl"]])
+                s["U"][a][s["nzl"] + 1].copy_(nxt["U"][a][1])
+        for i, s in enumerate(S):
+            U, P, nzl = s["U"], s["P"], s["nzl"]
+            check(lib.tmb_pd_tv_iter(ptr(s["data"]), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
+                                     ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
+                                     nzl, ny, nx, lam, methodTV, nonneg, lip, int(half), int(i > 0),
+                                     int(i + 1 < len(S)), stream_ptr(v)), "tmb_pd_tv_iter")
+    return torch.cat([s["U"][iters % 2][1:s["nzl"] + 1] for s in S], dim=0)
+
+
+@pytest.mark.parametrize("shape,cuts", [((40, 36, 64), [20]), ((45, 21, 132), [8, 30]), ((70, 16, 260), [2, 36]),
+                                        ((96, 8, 128), [48])])
+@pytest.mark.parametrize("methodTV,nonneg", [(0, 1), (1, 0)])
+@pytest.mark.parametrize("half", [False, True])
+def test_sharded_pd_tv_is_bit_identical(shape, cuts, methodTV, nonneg, half):
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy
+
+    v = _vol(shape, 11)
+    whole = PD_TV_cupy(v, 4e-4, 7, methodTV, nonneg, 12.0, 0, half)
+    parts = _sharded_prox(v, list(cuts), 4e-4, 7, methodTV, nonneg, 12.0, half)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
+    # and independent blocks (the reference under HTTomo's z-chunking) do differ at the seams
+    blocks = torch.cat([PD_TV_cupy(v[a:b].contiguous(), 4e-4, 7, methodTV, nonneg, 12.0, 0, half)
+                        for a, b in zip([0] + list(cuts), list(cuts) + [shape[0]])], dim=0)
+    assert not torch.equal(whole, blocks)
+
+
+def test_ghost_planes_need_the_strip_kernel():
+    from tomobar_b200._lib import lib
+    from tomobar_b200._tensors import ptr
+
+    v = _vol((6, 10, 30), 1)  # dx % 4 != 0
+    U = torch.zeros((8, 10, 30), device="cuda")
+    P = [torch.zeros((7, 10, 30), device="cuda") for _ in range(6)]
+    rc = lib.tmb_pd_tv_iter(ptr(v), ptr(U[1:]), ptr(torch.zeros_like(U)[1:]), *[ptr(p[1:]) for p in P], 6, 10, 30,
+                            1e-3, 0, 0, 12.0, 0, 1, 0, None)
+    assert rc == -3 and b"ghost" in lib.tmb_last_error()

@@ -18,7 +18,8 @@ def _vol(shape, seed):
     return v
 
 
-@pytest.mark.parametrize("shape", [(16, 70, 130), (80, 37, 200), (64, 129), (1, 50, 300)])
+@pytest.mark.parametrize("shape", [(16, 70, 130), (80, 37, 200), (64, 129), (1, 50, 300), (70, 21, 132), (96, 18, 64),
+                                   (9, 35, 388)])
 @pytest.mark.parametrize("methodTV,nonneg", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("half", [False, True])
 def test_pd_tv_vs_reference_kernel(shape, methodTV, nonneg, half):

@@ -36,6 +36,7 @@ SIGNATURES = {
     "tmb_tv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tmb_pd_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _i, _i, _f, _i, _vp, _vp]),
     "tmb_rof_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _f, _i, _vp, _vp]),
+    "tmb_pd_tv_iter": (_i, [_fp, _fp, _fp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _f, _i, _i, _i, _vp]),
     "tmb_tv_set_simple_kernels": (_i, [_i]),
     "tmb_fista_grad_step": (_i, [_fp, _fp, _fp, _sz, _f, _i, _vp]),
     "tmb_fista_momentum": (_i, [_fp, _fp, _fp, _sz, _f, _vp]),
@@ -45,6 +46,7 @@ SIGNATURES = {
     "tmb_sinc_filter": (_i, [_f, _fp, _i, _f, _vp]),
     "tmb_apply_filter": (_i, [_fp, _fp, _sz, _i, _vp]),
     "tmb_circular_mask": (_i, [_fp, _i, _i, _f, _vp]),
+    "tmb_normalise": (_i, [_vp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
     "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),
     "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
     "tmb_fi_gather": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _vp]),

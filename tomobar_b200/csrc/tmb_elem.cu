@@ -123,6 +123,31 @@ __global__ void k_mask(float *__restrict__ vol, int nz, int n, double limit) {
   for (int z = blockIdx.z; z < nz; z += gridDim.z) vol[((size_t)z * n + r) * n + c] = 0.f;
 }
 
+
+// flat / dark-field normalisation and negative log (supp/suppTools.py:187-264, "mean" / "median"
+// branch): one pass from the raw uint16 (or fp32) projections to the fp32 sinogram.
+// data is [n0][n1][n2] with the ANGLE axis 0 or 1; flat / dark are the averaged [.][n2] fields.
+template <typename TI>
+__global__ void k_normalise(const TI *__restrict__ data, const float *__restrict__ flat,
+                            const float *__restrict__ dark, float *__restrict__ out, size_t total, int n1, int n2,
+                            int angle_axis, int take_log) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t i2 = i % n2, i01 = i / n2;
+    const size_t row = angle_axis == 0 ? i01 % n1 : i01 / n1;  // index of the non-angle slow axis
+    const float d = __ldg(dark + row * n2 + i2);
+    float denom = __fsub_rn(__ldg(flat + row * n2 + i2), d);
+    if (denom <= 0.f) denom = 1.f;
+    float nomin = __fsub_rn((float)data[i], d);
+    if (nomin < 0.f) nomin = 1.f;
+    float v = __fdiv_rn(nomin, denom);
+    if (take_log) {
+      if (v > 0.f) v = -logf(v);
+      if (v < 0.f) v = 0.f;
+    }
+    out[i] = v;
+  }
+}
+
 }  // namespace tmb
 
 using namespace tmb;
@@ -185,4 +210,18 @@ extern "C" int tmb_circular_mask(float *vol, int nz, int n, float radius, void *
   dim3 grid((n + 127) / 128, n, nz < 64 ? nz : 64);
   k_mask<<<grid, 128, 0, (cudaStream_t)stream>>>(vol, nz, n, limit);
   return check_launch("k_mask");
+}
+
+extern "C" int tmb_normalise(const void *data, int data_is_u16, const float *flat_mean, const float *dark_mean,
+                             float *out, int n0, int n1, int n2, int angle_axis, int take_log, void *stream) {
+  TMB_REQUIRE(data && flat_mean && dark_mean && out, "tmb_normalise: null argument");
+  TMB_REQUIRE(n0 >= 1 && n1 >= 1 && n2 >= 1 && (angle_axis == 0 || angle_axis == 1), "tmb_normalise: bad argument");
+  const size_t total = (size_t)n0 * n1 * n2;
+  if (data_is_u16)
+    k_normalise<unsigned short><<<el_blocks(total), EL_THREADS, 0, (cudaStream_t)stream>>>(
+        static_cast<const unsigned short *>(data), flat_mean, dark_mean, out, total, n1, n2, angle_axis, take_log);
+  else
+    k_normalise<float><<<el_blocks(total), EL_THREADS, 0, (cudaStream_t)stream>>>(
+        static_cast<const float *>(data), flat_mean, dark_mean, out, total, n1, n2, angle_axis, take_log);
+  return check_launch("k_normalise");
 }

@@ -84,6 +84,18 @@ class RecToolsIRCuPy:
         self.data_fidelity = "LS"
         self.nonneg_regul = 0
         self.power_seed = 0  # the reference draws an unseeded cp.random.randn (:326)
+        self.zshard = None   # set_zshard(): this object reconstructs one z-block of a larger volume
+        self._sharded_tv = {}
+
+    def set_zshard(self, shard) -> None:
+        """Declare that this object holds the slices ``[shard.z0, shard.z1)`` of a volume that is
+        z-sharded over ``torch.distributed`` ranks (``tomobar_b200.zshard.ZShard``).  The norms of
+        the power method and of CGLS, the PWLS weight normalisation and the 3-D PD_TV prox then act
+        on the whole volume (scalar all-reduces, one-plane halo exchange per inner TV iteration)."""
+        if shard is not None and shard.nz_local != self.Atools.detectors_y:
+            raise ValueError("set_zshard: DetectorsDimV must equal the number of slices of the shard")
+        self.zshard = shard
+        self._sharded_tv = {}
 
     @property
     def OS_number(self) -> int:
@@ -128,6 +140,16 @@ class RecToolsIRCuPy:
 
     def _axpy(self, a: float, x: torch.Tensor, y: torch.Tensor, nonneg: bool = False) -> None:
         check(lib.tmb_axpy(float(a), ptr(x), ptr(y), _count(y), int(nonneg), self._stream()), "tmb_axpy")
+
+    def _norm(self, x: torch.Tensor) -> torch.Tensor:
+        if self.zshard is not None and self.zshard.world > 1:
+            return self.zshard.norm(x)
+        return torch.linalg.vector_norm(x.ravel())
+
+    def _dot(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        if self.zshard is not None and self.zshard.world > 1:
+            return self.zshard.dot(a, b)
+        return torch.inner(a.ravel(), b.ravel())
 
     def _subset_indices(self, sub_ind: int) -> np.ndarray:
         indVec = self.Atools.newInd_Vec[sub_ind, :]
@@ -174,15 +196,15 @@ class RecToolsIRCuPy:
         A = self.Atools
         x_rec = self._zeros_vol()
         d = A._backprojCuPy(b)
-        normr2 = torch.inner(d.ravel(), d.ravel())
+        normr2 = self._dot(d, d)
         r = b.clone()
         for _ in range(_algorithm_upd_["iterations"]):
             Ad = A._forwprojCuPy(d)
-            alpha = normr2 / torch.inner(Ad.ravel(), Ad.ravel())
+            alpha = normr2 / self._dot(Ad, Ad)
             x_rec += alpha * d
             r -= alpha * Ad
             s = A._backprojCuPy(r)
-            normr2_new = torch.inner(s.ravel(), s.ravel())
+            normr2_new = self._dot(s, s)
             beta = normr2_new / normr2
             normr2 = normr2_new
             d = s + beta * d
@@ -197,14 +219,14 @@ class RecToolsIRCuPy:
             _data_["data_fidelity"] = "LS"
         A = self.Atools
         gen = torch.Generator(device=A.device)
-        gen.manual_seed(self.power_seed)
+        gen.manual_seed(self.power_seed + (self.zshard.z0 if self.zshard is not None else 0))
         x1 = torch.randn(A.vol_geom, dtype=torch.float32, device=A.device, generator=gen)
         sub = 0 if self.OS_number > 1 else None
         s = 1.0
         y = A._forwprojOSCuPy(x1, 0) if sub is not None else A._forwprojCuPy(x1)
         for _ in range(15):
             x1 = A._backprojOSCuPy(y, 0) if sub is not None else A._backprojCuPy(y)
-            s = torch.linalg.vector_norm(x1.ravel())
+            s = self._norm(x1)
             x1 = x1 / s
             y = A._forwprojOSCuPy(x1, 0) if sub is not None else A._forwprojCuPy(x1)
         return float(s)
@@ -238,7 +260,8 @@ class RecToolsIRCuPy:
         w = None
         if _data_["data_fidelity"] in ["PWLS"]:
             w = torch.clamp(b, min=1e-6)  # weights for the PWLS model (:392-395)
-            w = w / w.max()
+            wmax = w.max() if self.zshard is None else self.zshard.max(w)
+            w = w / wmax
         return (_data_upd_, _algorithm_upd_, _regularisation_upd_, x0, w, use_os)
 
     def _prox_into(self, X: torch.Tensor, reg: dict, out: torch.Tensor) -> torch.Tensor:
@@ -248,6 +271,16 @@ class RecToolsIRCuPy:
             return ROF_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["time_marching_step"], dev,
                                reg.get("half_precision", False), out=out)
         if "PD_TV" in reg["method"]:
+            sh = self.zshard
+            if sh is not None and sh.world > 1 and X.ndim == 3 and min(X.shape) > 1:
+                # whole-volume 3-D TV across the z-shards: halo exchange between inner iterations
+                from tomobar_b200.zshard import ShardedPDTV
+
+                key = (tuple(X.shape), bool(reg.get("half_precision", False)))
+                if key not in self._sharded_tv:
+                    self._sharded_tv = {key: ShardedPDTV(sh, key[0], X.device, key[1])}
+                return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["methodTV"],
+                                             self.nonneg_regul, reg["PD_LipschitzConstant"], out=out)
             return PD_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["methodTV"], self.nonneg_regul,
                               reg["PD_LipschitzConstant"], dev, reg.get("half_precision", False), out=out)
         raise ValueError(f"Unknown regularisation method {reg['method']!r}: ROF_TV and PD_TV are supported")

@@ -1,8 +1,9 @@
-"""Detector padding, reconstruction cropping and circular masking on CUDA tensors
-(behaviour of tomobar/supp/suppTools.py:364-467)."""
+"""Detector padding, reconstruction cropping, circular masking and flat/dark-field normalisation on
+CUDA tensors (behaviour of tomobar/supp/suppTools.py:187-264, 364-467)."""
 
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from tomobar_b200._lib import lib, check
@@ -45,3 +46,47 @@ def check_kwargs(reconstruction: torch.Tensor, **kwargs) -> torch.Tensor:
         if key == "recon_mask_radius" and value is not None:
             apply_circular_mask(reconstruction, value, kwargs.get("cupyrun", True))
     return reconstruction
+
+
+def normaliser(data, flats, darks, log: bool = True, method: str = "mean", axis: int = 0, device=0,
+               **kwargs) -> torch.Tensor:
+    """Flat / dark-field normalisation with negative log (suppTools.py:187-264) in one fused pass
+    from the raw (uint16 or float32) projections to the float32 CUDA sinogram.
+
+    ``data`` is 3-D with the angle axis ``axis`` (0 or 1); ``flats`` / ``darks`` are stacks along the
+    same axis (``darks`` may be None).  Methods "mean" and "median"; the reference's "dynamic" flat
+    fielding (a CPU pre-processing routine) is not part of the hot path.
+    """
+    dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+
+    def to_dev(a):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        return a.to(dev)
+
+    data = to_dev(data)
+    if data.ndim == 2:
+        raise NameError("Normalisation is implemented for 3d data input")
+    if axis not in (0, 1):
+        raise ValueError("normaliser: the angle axis must be 0 or 1")
+    flats = to_dev(flats).to(torch.float32)
+    darks = torch.zeros_like(flats) if darks is None else to_dev(darks).to(torch.float32)
+    if method is None or method == "mean":
+        flat_m, dark_m = flats.mean(axis), darks.mean(axis)
+    elif method == "median":
+        flat_m, dark_m = flats.quantile(0.5, dim=axis), darks.quantile(0.5, dim=axis)
+    elif method == "dynamic":
+        raise NotImplementedError("dynamic flat-field correction is outside the GPU hot path")
+    else:
+        raise NameError("Please select an appropriate method for normalisation: mean, median or dynamic")
+    is_u16 = data.dtype == torch.uint16
+    if not is_u16:
+        data = data.to(torch.float32)
+    data = data.contiguous()
+    flat_m, dark_m = flat_m.contiguous(), dark_m.contiguous()
+    n0, n1, n2 = data.shape
+    out = torch.empty((n0, n1, n2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tmb_normalise(ptr(data), int(is_u16), ptr(flat_m), ptr(dark_m), ptr(out), n0, n1, n2, int(axis),
+                                int(bool(log)), stream_ptr(out)), "tmb_normalise")
+    return out

@@ -1,0 +1,173 @@
+"""z-sharding of the reconstruction over ``torch.distributed`` ranks (one process per GPU).
+
+For a scalar centre of rotation and a vertical rotation axis every slice is an independent 2-D
+problem for the projector pair, the FBP filter and FOURIER_INV (the reference relies on the caller,
+HTTomo, to chunk in z: docs/source/introduction/dependencies.rst:56-58).  Rank r owns the contiguous
+block of slices ``[z0, z1)`` of the volume and the same detector rows of the sinogram.  What couples
+the shards:
+
+* scalars: the power method's norm (methodsIR_CuPy.py:333-351), the PWLS weight normalisation
+  ``w.max()`` (:394-395), CGLS inner products (:270-289)  ->  one scalar all-reduce each;
+* 3-D total variation: the forward z difference and the backward z divergence reach one plane into
+  the neighbouring shards (primal_dual_for_total_variation.cu:188-194, 244-252).  ``ShardedPDTV``
+  keeps one ghost plane below / above the shard and refreshes it with point-to-point messages
+  between the inner iterations; the result is bit-identical to the whole-volume prox;
+* the final volume: one all-gather (``ZShard.all_gather_volume``).
+
+Nothing here touches the CUDA library except ``ShardedPDTV``; the rest runs on any backend
+(``gloo`` on CPU tensors in the unit tests, ``nccl`` on the GPUs).
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(nz: int, world: int, rank: int, multiple: int = 2) -> Tuple[int, int]:
+    """Contiguous block ``[z0, z1)`` of rank ``rank``.  Block sizes are multiples of ``multiple``
+    (FOURIER_INV processes slices in pairs, methodsDIR_CuPy.py:268-282) except the last non-empty one."""
+    if nz <= 0 or world <= 0 or not 0 <= rank < world or multiple <= 0:
+        raise ValueError("shard_bounds: bad arguments")
+    per = -(-nz // world)
+    per = -(-per // multiple) * multiple
+    z0 = min(nz, rank * per)
+    return z0, min(nz, z0 + per)
+
+
+class ZShard:
+    """The z-partition of one rank and the collectives the hot path needs."""
+
+    def __init__(self, nz_total: int, group: Optional[dist.ProcessGroup] = None, multiple: int = 2):
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.nz_total = int(nz_total)
+        self.multiple = multiple
+        self.z0, self.z1 = shard_bounds(self.nz_total, self.world, self.rank, multiple)
+        if self.z1 <= self.z0:
+            raise ValueError(f"rank {self.rank} of {self.world} owns no slices of {nz_total}: use fewer ranks")
+        # neighbours that own slices (trailing ranks may be empty only if the constructor raised there)
+        self.prev = self.rank - 1 if self.rank > 0 else None
+        self.next = self.rank + 1 if self.rank + 1 < self.world and self.z1 < self.nz_total else None
+
+    @property
+    def nz_local(self) -> int:
+        return self.z1 - self.z0
+
+    def _global(self, peer: int) -> int:
+        return dist.get_global_rank(self.group, peer) if self.group is not None else peer
+
+    # ---- scalars ------------------------------------------------------------------------------
+    def allreduce_(self, t: torch.Tensor, op=None) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op is None else op, group=self.group)
+        return t
+
+    def norm(self, x: torch.Tensor) -> torch.Tensor:
+        """Euclidean norm of the WHOLE (sharded) array; 0-dim tensor on x's device."""
+        s = torch.sum(x.double() * x.double())
+        return torch.sqrt(self.allreduce_(s)).to(torch.float32)
+
+    def dot(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return self.allreduce_(torch.sum(a.double() * b.double())).to(torch.float32)
+
+    def max(self, x: torch.Tensor) -> torch.Tensor:
+        return self.allreduce_(x.max().clone(), dist.ReduceOp.MAX)
+
+    def min(self, x: torch.Tensor) -> torch.Tensor:
+        return self.allreduce_(x.min().clone(), dist.ReduceOp.MIN)
+
+    # ---- halos ----------------------------------------------------------------------------------
+    def exchange_halos(self, up: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                       down: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> None:
+        """``up``: pairs (send, recv): ``send`` goes to the next rank, ``recv`` is filled by the
+        previous rank's ``send`` of the same pair.  ``down``: ``send`` goes to the previous rank,
+        ``recv`` is filled by the next rank.  All tensors contiguous; blocks until complete (on the
+        current CUDA stream for nccl)."""
+        if self.world == 1:
+            return
+        ops: List[dist.P2POp] = []
+        for send, recv in up:
+            if self.next is not None:
+                ops.append(dist.P2POp(dist.isend, send, self._global(self.next), self.group))
+            if self.prev is not None:
+                ops.append(dist.P2POp(dist.irecv, recv, self._global(self.prev), self.group))
+        for send, recv in down:
+            if self.prev is not None:
+                ops.append(dist.P2POp(dist.isend, send, self._global(self.prev), self.group))
+            if self.next is not None:
+                ops.append(dist.P2POp(dist.irecv, recv, self._global(self.next), self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    # ---- assembly -------------------------------------------------------------------------------
+    def all_gather_volume(self, x_local: torch.Tensor) -> torch.Tensor:
+        """All ranks receive the whole volume ``[nz_total, ...]`` (the single collective of the
+        projector / FBP / FOURIER_INV paths)."""
+        if self.world == 1:
+            return x_local
+        per = shard_bounds(self.nz_total, self.world, 0, self.multiple)[1]
+        tail = tuple(x_local.shape[1:])
+        padded = x_local
+        if x_local.shape[0] != per:  # last shard: pad to the common block size
+            padded = torch.zeros((per,) + tail, dtype=x_local.dtype, device=x_local.device)
+            padded[: x_local.shape[0]] = x_local
+        out = torch.empty((self.world * per,) + tail, dtype=x_local.dtype, device=x_local.device)
+        dist.all_gather_into_tensor(out, padded.contiguous(), group=self.group)
+        return out[: self.nz_total]
+
+
+class ShardedPDTV:
+    """PD_TV prox of a z-sharded 3-D volume, bit-identical to ``PD_TV_cupy`` on the whole volume.
+
+    Per inner iteration each rank sends its top plane of U and of P1..P3 to the next rank and its
+    bottom plane of U to the previous one (5 planes), then launches ``tmb_pd_tv_iter`` with the
+    ghost flags of its position.  Buffers are allocated once and reused across calls."""
+
+    def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False):
+        nzl, ny, nx = shape
+        if nzl != shard.nz_local:
+            raise ValueError("ShardedPDTV: the volume shard does not match the z-partition")
+        self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
+        pdt = torch.float16 if self.half else torch.float32
+        # U: ghost plane below (index 0) and above (index nzl + 1); P: ghost plane below only
+        self.U = [torch.zeros((nzl + 2, ny, nx), dtype=torch.float32, device=device) for _ in range(2)]
+        self.P = [[torch.zeros((nzl + 1, ny, nx), dtype=pdt, device=device) for _ in range(3)] for _ in range(2)]
+
+    def __call__(self, data: torch.Tensor, regularisation_parameter: float, iterations: int, methodTV: int = 0,
+                 nonneg: int = 0, lipschitz_const: float = 8.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from tomobar_b200._lib import lib, check
+        from tomobar_b200._tensors import ptr, stream_ptr
+
+        sh = self.shard
+        nzl, ny, nx = self.shape
+        if tuple(data.shape) != self.shape or data.dtype != torch.float32 or not data.is_contiguous():
+            raise ValueError(f"ShardedPDTV: expected a contiguous float32 volume shard of shape {self.shape}")
+        U, P = self.U, self.P
+        U[0][1:nzl + 1].copy_(data)
+        for c in range(3):
+            P[0][c].zero_()
+        ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
+        with torch.cuda.device(self.device):
+            for it in range(int(iterations)):
+                a, b = it % 2, 1 - it % 2
+                up = [(U[a][nzl], U[a][0])]
+                if it > 0:  # the dual variable starts at zero everywhere
+                    up += [(P[a][c][nzl], P[a][c][0]) for c in range(3)]
+                sh.exchange_halos(up, [(U[a][1], U[a][nzl + 1])])
+                check(lib.tmb_pd_tv_iter(ptr(data), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
+                                         ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
+                                         nzl, ny, nx, float(regularisation_parameter), int(methodTV), int(nonneg),
+                                         float(lipschitz_const), int(self.half), ghost_lo, ghost_hi,
+                                         stream_ptr(data)), "tmb_pd_tv_iter")
+        res = U[int(iterations) % 2][1:nzl + 1]
+        if out is None:
+            return res.clone()
+        out.copy_(res)
+        return out
