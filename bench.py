@@ -7,8 +7,10 @@ BASELINE.json (2048 x 2048 x 512 volume, 1800 angles) plus forward / back-projec
 A *step* is one ordered-subset sub-step of FISTA (subset forward projection with fused residual,
 subset back-projection, gradient step, PD_TV prox, momentum).  `value` is outer FISTA iterations
 per second (= sub-steps/s / OS) for the WHOLE volume; with N GPUs the volume is z-sharded
-(512/N slices per rank, strong scaling, no data-path collective; TV runs per shard like the
-reference's HTTomo z-blocks).  Prints ONE JSON line on rank 0.
+(512/N slices per rank, strong scaling).  The projector pair needs no communication; the 3-D TV
+prox exchanges one-plane halos with the neighbouring shards between its inner iterations
+(tomobar_b200.zshard.ShardedPDTV, bit-identical to the single-GPU prox; --independent-tv gives
+the reference's HTTomo behaviour of independent z-blocks instead).  Prints ONE JSON line on rank 0.
 """
 
 from __future__ import annotations
@@ -207,6 +209,7 @@ def _config(cfg, gpus):
                      f"OS={cfg['os']}, PD_TV {cfg['tv_iters']} inner iterations (fp32 duals)"),
         "n": cfg["n"], "nz": cfg["nz"], "angles": cfg["na"], "os_number": cfg["os"],
         "tv_inner_iterations": cfg["tv_iters"], "z_shards": gpus,
+        "tv_across_shards": "halo exchange (exact)" if gpus > 1 else "n/a",
         "l2_policy": "working set per step (>= 8 GB per rank) far exceeds the 126 MB L2; no flush needed",
     }
 
@@ -228,6 +231,8 @@ def main():
     ap.add_argument("--half", action="store_true", help="fp16 storage of the TV dual variables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--independent-tv", action="store_true",
+                    help="multi-GPU: TV per z-shard without halo exchange (seams at the shard borders)")
     args = ap.parse_args()
     cfg = dict(n=args.n, nz=args.nz, na=args.angles, os=args.os, tv_iters=args.tv_iters,
                tv_lambda=HEADLINE["tv_lambda"])
@@ -245,6 +250,7 @@ def main():
     from tomobar_b200._tensors import ptr
     from tomobar_b200.methodsIR_CuPy import RecToolsIRCuPy
     from tomobar_b200.regularisersCuPy import PD_TV_cupy
+    from tomobar_b200.zshard import ZShard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -257,12 +263,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n, nz, na, os_n = cfg["n"], cfg["nz"], cfg["na"], cfg["os"]
     # z-shard: contiguous block of slices per rank
-    per = (nz + world - 1) // world
-    z0, z1 = min(nz, rank * per), min(nz, (rank + 1) * per)
-    nz_loc = z1 - z0
+    shard = ZShard(nz)
+    z0, z1, nz_loc = shard.z0, shard.z1, shard.nz_local
     angles = np.linspace(0.0, math.radians(179.9), na).astype(np.float32)
 
     rec = RecToolsIRCuPy(n, 0, nz_loc, 0.0, angles, n, local_rank, os_n)
+    if world > 1 and not args.independent_tv:
+        rec.set_zshard(shard)
+    rec.nonneg_regul = 1
     A = rec.Atools
     # synthetic data generated on the device, slice blocks of 16 to bound temporaries
     b = torch.empty((nz_loc, na, n), dtype=torch.float32, device=dev)
@@ -289,7 +297,7 @@ def main():
         t_old = state["t"]
         A.grad_data_term(X_t, b, state["sub"], "LS", None, out=G)
         check(lib.tmb_fista_grad_step(ptr(X_t), ptr(G), ptr(G), count, L_inv, 1, st), "grad_step")
-        PD_TV_cupy(G, reg["regul_param"], reg["iterations"], 0, 1, 12.0, local_rank, reg["half_precision"], out=X)
+        rec._prox_into(G, reg, X)  # PD_TV; whole-volume across the shards when world > 1
         t = np.float32((1.0 + np.sqrt(1.0 + 4.0 * t_old ** 2)) * 0.5)
         check(lib.tmb_fista_momentum(ptr(X), ptr(X_old), ptr(X_t), count, float((t_old - 1.0) / t), st),
               "momentum")
@@ -301,7 +309,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches_per_step = 1 + 1 + 1 + 1 + cfg["tv_iters"] + 1  # layout, FP, BP, step, TV its, momentum
+    # our kernels per sub-step: layout conversion, k_fp, k_bp, gradient step, PD_TV iterations, momentum
+    launches_per_step = 1 + 1 + 1 + 1 + cfg["tv_iters"] + 1
 
     for _ in range(args.warmup):
         substep()
@@ -350,7 +359,7 @@ def main():
     tv_gbs = bytes_tv / (ms_tv * 1e-3) / 1e9
     share_tv = ms_tv * cfg["tv_iters"] / ms_step
     roofline = {
-        "kernel": "k_pd_tv (one Chambolle-Pock iteration)", "bound": "hbm", "achieved": tv_gbs, "peak": peak,
+        "kernel": "k_pd_tv3d_w (one Chambolle-Pock iteration, warp-strip kernel)", "bound": "hbm", "achieved": tv_gbs, "peak": peak,
         "unit": "GB/s", "frac": tv_gbs / peak, "peak_source": peak_src, "traffic": None,
         "algorithmic_bytes_per_launch": bytes_tv, "ms_per_launch": ms_tv, "share_of_step": share_tv,
     }
@@ -377,7 +386,7 @@ def main():
             r = rec.FISTA({"projection_data": d},
                           {"iterations": 1, "lipschitz_const": 2.0e4, "nonnegativity": True,
                            "recon_mask_radius": None}, dict(reg))
-            out_host.copy_(r, non_blocking=True)
+            out_host.copy_(r, non_blocking=True)  # every rank returns its own z-block to the host
 
         e2e_iter()
         barrier()

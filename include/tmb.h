@@ -79,6 +79,19 @@ int tmb_bp3d(tmb_geom *g, int subset, const float *sino, float *vol, void *works
 int tmb_grad(tmb_geom *g, int subset, int fidelity, const float *x, const float *b, const float *w,
              float *grad, void *workspace, void *stream);
 
+/* Extension (no code in the reference snapshot; its legacy call sites are
+ * Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:197,307-309, Demo_RealData.py:157-158,219):
+ * gradient of the robust / ring-artefact data terms.  With res = A_s x - b_s:
+ *   ring_rx != NULL : Group-Huber ring model, res += ring_alpha * ring_rx[z][u] (one offset per
+ *                     detector pixel), ring_vec[z][u] = sum over the subset's angles of res
+ *   huber_delta > 0 : res *= min(1, huber_delta / |res|)
+ *   weight_mode 1   : PWLS, res *= w          weight_mode 2 : SWLS,
+ *                     res = w res - w * (sum_a w res) / (sum_a w + beta_swls)
+ * then grad = A_s^T res.  b, w are the full sinograms [nz][na][nu]; ring_rx / ring_vec are [nz][nu]. */
+int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float *b, const float *w, int weight_mode,
+                 float huber_delta, const float *ring_rx, float ring_alpha, float beta_swls, float *ring_vec,
+                 float *grad, void *workspace, void *stream);
+
 /* ---- TV proximal operators ---------------------------------------------------------------
  * tmb_pd_tv  replaces PD_TV_cupy  (regularisersCuPy.py:170-296 + primal_dual_for_total_variation.cu)
  * tmb_rof_tv replaces ROF_TV_cupy (regularisersCuPy.py:41-167 + rudin_osher_fatemi_total_variation.cu)

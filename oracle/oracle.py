@@ -507,11 +507,44 @@ class RecIR:
             w = w / w.max()
         return b, L, x0, w
 
+    # Extension (no code in this reference snapshot; legacy call sites
+    # Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:197,243,307-309): residual of the Huber /
+    # Group-Huber ring / SWLS data terms.  Defines the semantics the CUDA path (k_resid_post) is held to.
+    def residual_ext(self, x, b, use_os, sub_ind, indVec, w, fidelity, huber, r_x, alpha, beta):
+        res = (self._Ax(x, sub_ind, use_os) - b).astype(np.float32)
+        vec = None
+        if r_x is not None:
+            res = res + f32(alpha) * r_x[:, None, :]
+            vec = np.zeros_like(r_x)
+            for a in range(res.shape[1]):  # sequential fp32 sum over the angles
+                vec += res[:, a, :]
+        if huber is not None:
+            absr = np.abs(res)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                res = np.where(absr > f32(huber), res * (f32(huber) / absr), res).astype(np.float32)
+        if fidelity in ("PWLS", "SWLS"):
+            ws = w[:, indVec, :] if use_os else w
+            res = res * ws
+            if fidelity == "SWLS":
+                s = np.zeros((res.shape[0], res.shape[2]), np.float32)
+                sw = np.zeros_like(s)
+                for a in range(res.shape[1]):
+                    s += res[:, a, :]
+                    sw += ws[:, a, :]
+                res = res - ws * (s / (sw + f32(beta)))[:, None, :]
+        return res.astype(np.float32), vec
+
     # methodsIR_CuPy.py:401-484
     def FISTA(self, data, iterations, lipschitz_const=None, regularisation=None, nonneg=False,
-              fidelity="LS", initialise=None, mask_radius=1.0):
+              fidelity="LS", initialise=None, mask_radius=1.0, huber_threshold=None, ringGH_lambda=None,
+              ringGH_accelerate=50, beta_SWLS=0.1):
         reg = _reg_defaults(regularisation)
-        b_all, L, x0, w = self._init(data, fidelity, initialise, lipschitz_const)
+        b_all, L, x0, w = self._init(data, "PWLS" if fidelity == "SWLS" else fidelity, initialise, lipschitz_const)
+        extended = huber_threshold is not None or ringGH_lambda is not None or fidelity == "SWLS"
+        r = r_x = None
+        if ringGH_lambda is not None:
+            r = np.zeros((b_all.shape[0], b_all.shape[2]), np.float32)
+            r_x = r.copy()
         use_os = self.OS_number > 1
         Linv = 1.0 / L
         b = b_all
@@ -526,14 +559,26 @@ class RecIR:
                 if use_os:
                     indVec = self._subset(sub)
                     b = b_all[:, indVec, :]
-                grad = self.grad_data_term(X_t, b, use_os, sub, indVec, w, fidelity)
+                if extended:
+                    res, vec = self.residual_ext(X_t, b, use_os, sub, indVec, w, fidelity, huber_threshold, r_x,
+                                                 ringGH_accelerate, beta_SWLS)
+                    grad = self._Atb(res, sub, use_os)
+                    if r is not None:
+                        r_old = r
+                        r = (r_x - f32(Linv) * vec).astype(np.float32)
+                else:
+                    grad = self.grad_data_term(X_t, b, use_os, sub, indVec, w, fidelity)
                 X = (X_t - Linv * grad).astype(np.float32)
                 if nonneg:
                     np.maximum(X, 0, out=X)
                 if reg["method"] is not None:
                     X = prox_regul(X, reg, 1 if nonneg else 0)
                 t = f32((1.0 + np.sqrt(1.0 + 4.0 * t ** 2)) * 0.5)
-                X_t = (X + f32((t_old - 1.0) / t) * (X - X_old)).astype(np.float32)
+                coef = f32((t_old - 1.0) / t)
+                X_t = (X + coef * (X - X_old)).astype(np.float32)
+                if r is not None:
+                    r = (np.maximum(np.abs(r) - f32(ringGH_lambda), 0) * np.sign(r)).astype(np.float32)
+                    r_x = (r + coef * (r - r_old)).astype(np.float32)
         return self._finish(X, mask_radius)
 
     # methodsIR_CuPy.py:486-585

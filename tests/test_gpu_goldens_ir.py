@@ -15,7 +15,15 @@ pytestmark = pytest.mark.gpu
 
 # case -> {key: rtol} where the restated projector model does not reach the reference's own
 # tolerance (ASTRA's arithmetic is not in the reference tree)
-LOOSER = {}
+# measured on B200 (tools/golden_report.py, profiles/golden_report_r01.txt): every TV-regularised and
+# every ADMM case meets the reference's own tolerance; the un-regularised, ill-conditioned runs drift
+# by a few 1e-4 on the (tiny, negative) minimum
+LOOSER = {
+    "cgls_pad50_mask2": {"min": 1.5e-3, "max": 1e-3},     # 15 CG steps: got 6.8e-4 / 4.0e-4
+    "fista_2d_x50": {"min": 1e-3, "max": 5e-5},           # reference rtol 1e-6; got 4.2e-4 / 1.0e-5
+    "fista_os5_2d": {"min": 1e-3, "max": 5e-5},           # reference rtol 1e-6; got 4.3e-4 / 9.5e-6
+    "fista_os5_roftv_3d": {"min": 3e-4},                  # got 1.08e-4 on the minimum
+}
 
 
 @pytest.fixture(scope="module")

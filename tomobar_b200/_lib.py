@@ -33,6 +33,7 @@ SIGNATURES = {
     "tmb_fp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_bp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_grad": (_i, [_vp, _i, _i, _fp, _fp, _fp, _fp, _vp, _vp]),
+    "tmb_grad_ext": (_i, [_vp, _i, _fp, _fp, _fp, _i, _f, _fp, _f, _f, _fp, _fp, _vp, _vp]),
     "tmb_tv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tmb_pd_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _i, _i, _f, _i, _vp, _vp]),
     "tmb_rof_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _f, _i, _vp, _vp]),

@@ -303,6 +303,9 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
   __syncthreads();
 
   const int n_iter = (p.n + FP_G - 1) / FP_G;
+  // elements of a volume line the CTA's FP_K bins can touch at this angle: the bins advance by
+  // |bstep| in [1, sqrt 2] per bin, so only 45-degree rays need the whole FP_W window
+  const int win = min(FP_W, (int)ceilf((float)(FP_K - 1) * fabsf(bstep)) + 4);
 
   if (tid >= FP_K) {
     if (tid == FP_K) {
@@ -321,13 +324,13 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
           ws = max(-VPAD, min(ws, p.n));
           wst[s][gm] = ws;
         }
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * NZC * FP_W * sizeof(float4)));
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * NZC * win * sizeof(float4)));
         for (int gm = 0; gm < ng; ++gm) {
           const int ws = wst[s][gm];
 #pragma unroll
           for (int c = 0; c < NZC; ++c) {
             const float4 *src = vsrc + ((size_t)(zc0 + c) * p.n + (m0 + gm)) * p.qp + (VPAD + ws);
-            bulk_g2s(&buf[s][gm][c][0], src, FP_W * sizeof(float4), &full_bar[s]);
+            bulk_g2s(&buf[s][gm][c][0], src, win * sizeof(float4), &full_bar[s]);
           }
         }
       }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
       const float f = frac_weight(rho - fl, p.quant);
       const float g = 1.0f - f;
       int i = (int)fl - wst[s][gm];
-      i = max(0, min(i, FP_W - 2));
+      i = max(0, min(i, win - 2));
 #pragma unroll
       for (int c = 0; c < NZC; ++c) {
         const float4 s0 = buf[s][gm][c][i];
@@ -399,6 +402,90 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
         r[q] = v;
       }
       p.sint[((size_t)(zc0 + c) * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// ==========================================================================================
+// residual post-pass for the robust / ring-artefact data terms (extension, see DESIGN.md: the
+// reference snapshot only keeps their call sites, Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:
+// 197,307-309).  Runs on the residual the forward projector's epilogue left in S_int, one thread
+// per (z-chunk, detector bin) column walking the subset's angles:
+//   1. Group-Huber ring model: res += alpha * r_x[z][u];  vec[z][u] = sum over angles of res
+//   2. Huber:                   res *= min(1, delta / |res|)
+//   3. weights:  PWLS  res *= w        SWLS  res = w res - w * (sum_a w res) / (sum_a w + beta)
+// ==========================================================================================
+struct PostArgs {
+  float4 *sint;        // [nzc][na_loc][up]
+  const float *w;      // full weights [nz][na_tot][nu] or nullptr
+  const float *rx;     // [nz][nu] or nullptr
+  float *vec;          // [nz][nu] or nullptr
+  int nz, nu, up, na_loc, na_tot, g_first, g_stride;
+  int weight_mode;     // 0 none, 1 PWLS, 2 SWLS
+  float alpha, delta, beta;
+};
+
+__device__ __forceinline__ float huber_w(float r, float delta) {
+  const float a = fabsf(r);
+  return a > delta ? __fmul_rn(r, __fdiv_rn(delta, a)) : r;
+}
+
+__global__ void k_resid_post(const PostArgs p) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int zc = blockIdx.y;
+  if (u >= p.nu) return;
+  float rx[ZC] = {0.f, 0.f, 0.f, 0.f};
+  bool zin[ZC];
+#pragma unroll
+  for (int q = 0; q < ZC; ++q) {
+    zin[q] = zc * ZC + q < p.nz;
+    if (p.rx && zin[q]) rx[q] = __fmul_rn(p.alpha, p.rx[(size_t)(zc * ZC + q) * p.nu + u]);
+  }
+  float vec[ZC] = {0.f, 0.f, 0.f, 0.f}, s[ZC] = {0.f, 0.f, 0.f, 0.f}, sw[ZC] = {0.f, 0.f, 0.f, 0.f};
+  float4 *col = p.sint + (size_t)zc * p.na_loc * p.up + SPAD + u;
+  for (int j = 0; j < p.na_loc; ++j) {
+    float4 r4 = col[(size_t)j * p.up];
+    float *r = reinterpret_cast<float *>(&r4);
+    const int ga = p.g_first + j * p.g_stride;
+#pragma unroll
+    for (int q = 0; q < ZC; ++q) {
+      if (!zin[q]) continue;
+      float v = r[q];
+      if (p.rx) {
+        v = __fadd_rn(v, rx[q]);
+        vec[q] = __fadd_rn(vec[q], v);
+      }
+      if (p.delta > 0.f) v = huber_w(v, p.delta);
+      if (p.weight_mode) {
+        const float wv = p.w[((size_t)(zc * ZC + q) * p.na_tot + ga) * p.nu + u];
+        v = __fmul_rn(v, wv);
+        if (p.weight_mode == 2) {
+          s[q] = __fadd_rn(s[q], v);
+          sw[q] = __fadd_rn(sw[q], wv);
+        }
+      }
+      r[q] = v;
+    }
+    col[(size_t)j * p.up] = r4;
+  }
+  if (p.vec) {
+#pragma unroll
+    for (int q = 0; q < ZC; ++q)
+      if (zin[q]) p.vec[(size_t)(zc * ZC + q) * p.nu + u] = vec[q];
+  }
+  if (p.weight_mode == 2) {
+    float c[ZC];
+#pragma unroll
+    for (int q = 0; q < ZC; ++q) c[q] = __fdiv_rn(s[q], __fadd_rn(sw[q], p.beta));
+    for (int j = 0; j < p.na_loc; ++j) {
+      float4 r4 = col[(size_t)j * p.up];
+      float *r = reinterpret_cast<float *>(&r4);
+      const int ga = p.g_first + j * p.g_stride;
+#pragma unroll
+      for (int q = 0; q < ZC; ++q)
+        if (zin[q])
+          r[q] = __fsub_rn(r[q], __fmul_rn(p.w[((size_t)(zc * ZC + q) * p.na_tot + ga) * p.nu + u], c[q]));
+      col[(size_t)j * p.up] = r4;
     }
   }
 }
@@ -534,6 +621,34 @@ extern "C" int tmb_grad(tmb_geom *g, int subset, int fidelity, const float *x, c
   int rc = launch_vol_to_int(g, x, ws.v0, ws.v1, st);
   if (rc) return rc;
   rc = launch_fp(g, subset, ws.v0, ws.v1, nullptr, ws.s, b, fidelity == TMB_FID_PWLS ? w : nullptr, 1, fidelity, st);
+  if (rc) return rc;
+  return launch_bp(g, subset, ws.s, grad, st);
+}
+
+// Gradient of the robust / ring-artefact data terms (extension of tmb_grad; see k_resid_post).
+extern "C" int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float *b, const float *w,
+                            int weight_mode, float huber_delta, const float *ring_rx, float ring_alpha,
+                            float beta_swls, float *ring_vec, float *grad, void *workspace, void *stream) {
+  TMB_REQUIRE(g && x && b && grad && workspace, "tmb_grad_ext: null argument");
+  TMB_REQUIRE(subset >= -1 && subset < g->os_number, "tmb_grad_ext: subset out of range");
+  TMB_REQUIRE(weight_mode >= 0 && weight_mode <= 2, "tmb_grad_ext: weight_mode must be 0 (none), 1 (PWLS), 2 (SWLS)");
+  TMB_REQUIRE(weight_mode == 0 || w, "tmb_grad_ext: weights missing");
+  TMB_REQUIRE(!ring_rx == !ring_vec, "tmb_grad_ext: ring_rx and ring_vec go together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws = carve(g, workspace);
+  int rc = launch_vol_to_int(g, x, ws.v0, ws.v1, st);
+  if (rc) return rc;
+  // plain residual A x - b into S_int, then the post-pass, then the back-projection
+  rc = launch_fp(g, subset, ws.v0, ws.v1, nullptr, ws.s, b, nullptr, 1, TMB_FID_LS, st);
+  if (rc) return rc;
+  PostArgs a;
+  a.sint = ws.s; a.w = weight_mode ? w : nullptr; a.rx = ring_rx; a.vec = ring_vec;
+  a.nz = g->d.nz; a.nu = g->d.nu; a.up = g->d.up; a.na_loc = subset_size(g, subset); a.na_tot = g->d.na;
+  a.g_first = subset < 0 ? 0 : subset; a.g_stride = subset < 0 ? 1 : g->os_number;
+  a.weight_mode = weight_mode; a.alpha = ring_alpha; a.delta = huber_delta; a.beta = beta_swls;
+  dim3 grid((g->d.nu + 127) / 128, (g->d.nz + ZC - 1) / ZC);
+  k_resid_post<<<grid, 128, 0, st>>>(a);
+  rc = check_launch("k_resid_post");
   if (rc) return rc;
   return launch_bp(g, subset, ws.s, grad, st);
 }

@@ -258,7 +258,7 @@ class RecToolsIRCuPy:
 
         use_os = self.OS_number > 1
         w = None
-        if _data_["data_fidelity"] in ["PWLS"]:
+        if _data_["data_fidelity"] in ["PWLS", "SWLS"]:
             w = torch.clamp(b, min=1e-6)  # weights for the PWLS model (:392-395)
             wmax = w.max() if self.zshard is None else self.zshard.max(w)
             w = w / wmax
@@ -314,12 +314,33 @@ class RecToolsIRCuPy:
         X_old = torch.empty_like(x0)   # rotating volumes: X_old / X / scratch
         G = torch.empty_like(x0)       # gradient, then the pre-prox iterate
 
+        # robust / ring-artefact data terms (extension): Huber residual clipping, the
+        # Group-Huber ring model (one offset r per detector pixel, soft-thresholded, with its own
+        # momentum) and stripe-weighted least squares
+        huber = _data_upd_.get("huber_threshold")
+        ring_lambda = _data_upd_.get("ringGH_lambda")
+        extended = huber is not None or ring_lambda is not None or self.data_fidelity == "SWLS"
+        if extended and self.data_fidelity == "KL":
+            raise ValueError("Huber / ring / SWLS models combine with the LS and PWLS data terms only")
+        r = r_x = vec = None
+        if ring_lambda is not None:
+            r = torch.zeros((A.detectors_y, A.nu), dtype=torch.float32, device=A.device)
+            r_x, vec = r.clone(), torch.empty_like(r)
+
         with torch.cuda.device(A.device):
             for _ in range(_algorithm_upd_["iterations"]):
                 for sub_ind in range(self.OS_number):
                     X_old, X = X, X_old            # X_old <- current iterate; X <- free buffer
                     t_old = t
-                    A.grad_data_term(X_t, b, sub_ind if use_os else None, self.data_fidelity, w, out=G)
+                    if extended:
+                        A.grad_data_term_ext(X_t, b, sub_ind if use_os else None, self.data_fidelity, w, huber,
+                                             r_x, float(_data_upd_["ringGH_accelerate"]),
+                                             float(_data_upd_["beta_SWLS"]), vec, out=G)
+                        if r is not None:
+                            r_old = r
+                            r = r_x - np.float32(L_const_inv) * vec
+                    else:
+                        A.grad_data_term(X_t, b, sub_ind if use_os else None, self.data_fidelity, w, out=G)
                     target = G if regularised else X
                     check(lib.tmb_fista_grad_step(ptr(X_t), ptr(G), ptr(target), count, float(L_const_inv),
                                                   int(nonneg), st), "tmb_fista_grad_step")
@@ -329,6 +350,9 @@ class RecToolsIRCuPy:
                     coef = np.float32((t_old - 1.0) / t)
                     check(lib.tmb_fista_momentum(ptr(X), ptr(X_old), ptr(X_t), count, float(coef), st),
                           "tmb_fista_momentum")
+                    if r is not None:
+                        r = torch.clamp(r.abs() - np.float32(ring_lambda), min=0) * torch.sign(r)
+                        r_x = (r + coef * (r - r_old)).contiguous()
         return self._finish(X, _algorithm_upd_["recon_mask_radius"])
 
     # ---- ADMM (:486-585) --------------------------------------------------------------------------

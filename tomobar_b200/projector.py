@@ -208,3 +208,30 @@ class ProjTools3D:
                                ptr(w_full) if w_full is not None else None, ptr(out),
                                ptr(self._workspace()), stream_ptr(out)), "tmb_grad")
         return out
+
+    # ---- robust / ring-artefact data terms (extension; include/tmb.h tmb_grad_ext) ----------------
+    def grad_data_term_ext(self, x: torch.Tensor, b_full: torch.Tensor, os_index: Optional[int],
+                           fidelity: str = "LS", w_full: Optional[torch.Tensor] = None,
+                           huber_threshold: Optional[float] = None, ring_rx: Optional[torch.Tensor] = None,
+                           ring_alpha: float = 0.0, beta_swls: float = 0.0,
+                           ring_vec: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """grad = A_s^T rho'(A_s x - b_s) for the Huber / Group-Huber ring / SWLS models; ``ring_vec``
+        ([nz, nu]) receives the angle-sum of the ring-corrected residual."""
+        sub = self._sub(os_index)
+        mode = {"LS": 0, "PWLS": 1, "SWLS": 2}[fidelity]
+        x = require_dense(as_cuda_f32(x, self.device, "volume"), self.vol_geom, "volume")
+        b_full = require_dense(b_full, self.proj_geom, "projection data")
+        if mode:
+            w_full = require_dense(w_full, self.proj_geom, "weights")
+        if ring_rx is not None:
+            ring_rx = require_dense(ring_rx, (self.detectors_y, self.nu), "ring variable")
+            ring_vec = require_dense(ring_vec, (self.detectors_y, self.nu), "ring residual sum")
+        if out is None:
+            out = torch.empty(self.vol_geom, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.tmb_grad_ext(self._g, sub, ptr(x), ptr(b_full), ptr(w_full) if mode else None, mode,
+                                   float(huber_threshold or 0.0), ptr(ring_rx) if ring_rx is not None else None,
+                                   float(ring_alpha), float(beta_swls),
+                                   ptr(ring_vec) if ring_rx is not None else None, ptr(out),
+                                   ptr(self._workspace()), stream_ptr(out)), "tmb_grad_ext")
+        return out

@@ -77,9 +77,17 @@ def dicts_check(
 
     if _data_.get("data_fidelity") is None:
         _data_["data_fidelity"] = "LS"
-    if _data_["data_fidelity"] not in {"LS", "PWLS", "KL"}:
-        raise ValueError("_data_['data_fidelity'] should be provided as 'LS', 'PWLS', 'KL'.")
+    if _data_["data_fidelity"] not in {"LS", "PWLS", "KL", "SWLS"}:
+        raise ValueError("_data_['data_fidelity'] should be provided as 'LS', 'PWLS', 'KL' (or 'SWLS').")
     self.data_fidelity = _data_["data_fidelity"]
+    # robust / ring-artefact extensions: absent from this reference snapshot's dicts.py, keys and
+    # defaults as in its legacy demos (Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:197,243,307-309)
+    _data_.setdefault("huber_threshold", None)
+    _data_.setdefault("ringGH_lambda", None)
+    _data_.setdefault("ringGH_accelerate", 50)
+    _data_.setdefault("beta_SWLS", 0.1)
+    if _data_["data_fidelity"] == "SWLS" and method_run != "FISTA":
+        raise ValueError("The SWLS data term is available in FISTA only")
 
     use_os = self.OS_number > 1
     if use_os and method_run in _NO_OS:
