@@ -117,9 +117,17 @@ int tmb_pd_tv_iter(const float *in, const float *u_in, float *u_out, const void 
                    float regularisation_parameter, int methodTV, int nonneg, float lipschitz_const,
                    int half_precision, int ghost_lo, int ghost_hi, void *stream);
 
+/* One ROF iteration on caller-owned ping-pong buffers (rudin_osher_fatemi_total_variation.cu:157-248,
+ * both kernels fused; regularisersCuPy.py:112-162 launches them per iteration).  z-SHARDS: with
+ * ghost_hi plane dz of u_in must exist; with ghost_lo planes -2 and -1 must exist (the normalised z
+ * difference of plane -1 enters the divergence at plane 0).  Needs dx % 4 == 0 and aligned arrays. */
+int tmb_rof_tv_iter(const float *in, const float *u_in, float *u_out, int dz, int dy, int dx,
+                    float regularisation_parameter, float time_marching_parameter, int half_precision,
+                    int ghost_lo, int ghost_hi, void *stream);
+
 /* Debug/test switch: 1 routes 3-D TV through the simple one-thread-per-voxel kernels instead of
- * the z-marching ones, 2 through the CTA-tiled z-marching kernels, 3 through the register-fed
- * warp-strip kernels instead of the TMA-fed ones (same arithmetic; used by the parity tests).
+ * the z-marching ones, 2 through the CTA-tiled z-marching kernels, 3 / 4 force the register-fed / TMA-fed
+ * warp-strip PD_TV kernel (0 picks the measured best; same arithmetic, used by the parity tests).
  * Returns the old value. */
 int tmb_tv_set_simple_kernels(int enable);
 

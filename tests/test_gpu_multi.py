@@ -21,7 +21,8 @@ def _worker(rank, world, init_file, results):
     try:
         from tomobar_b200.methodsIR_CuPy import RecToolsIRCuPy
         from tomobar_b200.regularisersCuPy import PD_TV_cupy
-        from tomobar_b200.zshard import ShardedPDTV, ZShard
+        from tomobar_b200.regularisersCuPy import ROF_TV_cupy
+        from tomobar_b200.zshard import ShardedPDTV, ShardedROFTV, ZShard
 
         nz, n, na = 24, 64, 48
         sh = ZShard(nz)
@@ -36,6 +37,9 @@ def _worker(rank, world, init_file, results):
             whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
             gathered = sh.all_gather_volume(part)
             out[f"tv_equal_half{int(half)}"] = bool(torch.equal(gathered, whole))
+        rof = ShardedROFTV(sh, (sh.nz_local, n, n), dev, False)
+        part = rof(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 1e-3)
+        out["rof_equal"] = bool(torch.equal(sh.all_gather_volume(part), ROF_TV_cupy(full, 4e-4, 9, 1e-3, rank, False)))
         # --- sharded FISTA-OS + PD_TV == whole-volume run ------------------------------------------
         angles = np.linspace(0, np.pi, na, endpoint=False).astype(np.float32)
         sino = torch.rand((nz, na, n), generator=g).to(dev)
@@ -48,6 +52,13 @@ def _worker(rank, world, init_file, results):
         ref = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, rank, 4).FISTA({"projection_data": sino}, dict(alg), dict(reg))
         out["fista_equal"] = bool(torch.equal(x_all, ref))
         out["fista_maxdiff"] = float((x_all - ref).abs().max())
+        # --- sharded ADMM-OS + ROF_TV == whole-volume run (BASELINE.json config 3 in miniature) ----------
+        aalg = {"iterations": 3, "lipschitz_const": 2000.0, "ADMM_rho_const": 1.0, "ADMM_relax_par": 1.7,
+                "recon_mask_radius": None}
+        areg = {"method": "ROF_TV", "regul_param": 3e-4, "iterations": 6, "time_marching_step": 1e-3}
+        a_loc = rec.ADMM({"projection_data": sino[sh.z0:sh.z1].contiguous()}, dict(aalg), dict(areg))
+        a_ref = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, rank, 4).ADMM({"projection_data": sino}, dict(aalg), dict(areg))
+        out["admm_equal"] = bool(torch.equal(sh.all_gather_volume(a_loc.contiguous()), a_ref))
         # --- sharded power method ~ whole-volume power method ---------------------------------------
         out["L_sharded"] = rec.powermethod({"projection_data": sino[sh.z0:sh.z1].contiguous()})
         out["L_whole"] = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, rank, 4).powermethod({"projection_data": sino})
@@ -64,6 +75,8 @@ def test_two_gpu_sharded_tv_and_fista():
     for r in range(2):
         res = results[r]
         assert res["tv_equal_half0"] and res["tv_equal_half1"], res
+        assert res["rof_equal"], res
         assert res["fista_equal"], res
+        assert res["admm_equal"], res
         assert res["L_sharded"] == pytest.approx(res["L_whole"], rel=1e-3)
     assert results[0]["L_sharded"] == results[1]["L_sharded"]

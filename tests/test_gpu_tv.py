@@ -69,14 +69,14 @@ def test_tv_errors_and_edge_cases():
 @pytest.mark.parametrize("shape", [(70, 100, 150), (33, 9, 65), (64, 64, 64), (97, 35, 260), (130, 5, 128), (40, 64, 8)])
 @pytest.mark.parametrize("half", [False, True])
 def test_marching_kernels_match_simple_kernels(shape, half):
-    """The warp-strip kernels (dx % 4 == 0; TMA-fed = mode 0, register-fed = mode 3), the CTA-tiled
+    """The warp-strip kernels (dx % 4 == 0; register-fed = mode 3, TMA-fed = mode 4), the CTA-tiled
     z-marching kernels (mode 2) and the one-thread-per-voxel kernels (mode 1) share their arithmetic."""
     from tomobar_b200._lib import lib
     from tomobar_b200.regularisersCuPy import PD_TV_cupy, ROF_TV_cupy
 
     v = torch.from_numpy(_vol(shape, 7)).cuda()
     res = {}
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 4):
         old = lib.tmb_tv_set_simple_kernels(mode)
         try:
             res[mode] = (PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half).cpu().numpy(),
@@ -85,6 +85,6 @@ def test_marching_kernels_match_simple_kernels(shape, half):
         finally:
             lib.tmb_tv_set_simple_kernels(old)
     tol = 2e-3 if half else 2e-6
-    for mode in (0, 2, 3):
+    for mode in (0, 2, 3, 4):
         for a, b in zip(res[mode], res[1]):
             assert rel_max(a, b) < tol

@@ -67,6 +67,45 @@ def test_sharded_pd_tv_is_bit_identical(shape, cuts, methodTV, nonneg, half):
     assert not torch.equal(whole, blocks)
 
 
+def _sharded_rof(v, cuts, lam, iters, tau, half):
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr, stream_ptr
+
+    nz, ny, nx = v.shape
+    bounds = list(zip([0] + cuts, cuts + [nz]))
+    S = []
+    for (z0, z1) in bounds:
+        nzl = z1 - z0
+        U = [torch.zeros((nzl + 3, ny, nx), device="cuda") for _ in range(2)]
+        U[0][2:nzl + 2] = v[z0:z1]
+        S.append(dict(nzl=nzl, U=U, data=v[z0:z1].contiguous()))
+    for it in range(iters):
+        a, b = it % 2, 1 - it % 2
+        for i, s in enumerate(S):
+            if i + 1 < len(S):
+                nxt = S[i + 1]
+                nxt["U"][a][0:2].copy_(s["U"][a][s["nzl"]:s["nzl"] + 2])
+                s["U"][a][s["nzl"] + 2].copy_(nxt["U"][a][2])
+        for i, s in enumerate(S):
+            U, nzl = s["U"], s["nzl"]
+            check(lib.tmb_rof_tv_iter(ptr(s["data"]), ptr(U[a][2:]), ptr(U[b][2:]), nzl, ny, nx, lam, tau, int(half),
+                                      int(i > 0), int(i + 1 < len(S)), stream_ptr(v)), "tmb_rof_tv_iter")
+    return torch.cat([s["U"][iters % 2][2:s["nzl"] + 2] for s in S], dim=0)
+
+
+@pytest.mark.parametrize("shape,cuts", [((40, 36, 64), [20]), ((45, 21, 132), [8, 30]), ((70, 16, 260), [2, 36]),
+                                        ((96, 8, 128), [48])])
+@pytest.mark.parametrize("half", [False, True])
+def test_sharded_rof_tv_is_bit_identical(shape, cuts, half):
+    from tomobar_b200.regularisersCuPy import ROF_TV_cupy
+
+    v = _vol(shape, 12)
+    whole = ROF_TV_cupy(v, 4e-4, 7, 1e-3, 0, half)
+    parts = _sharded_rof(v, list(cuts), 4e-4, 7, 1e-3, half)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
+
+
 def test_ghost_planes_need_the_strip_kernel():
     from tomobar_b200._lib import lib
     from tomobar_b200._tensors import ptr

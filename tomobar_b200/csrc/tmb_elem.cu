@@ -6,6 +6,10 @@ namespace tmb {
 
 constexpr int EL_THREADS = 256;
 
+static inline bool aligned16(const void *a, const void *b, const void *c) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
 static inline int el_blocks(size_t count) {
   size_t b = (count + EL_THREADS - 1) / EL_THREADS;
   const size_t cap = 148 * 16;  // grid-stride: 16 resident CTAs on each of the 148 SMs
@@ -14,22 +18,41 @@ static inline int el_blocks(size_t count) {
 
 // X = X_t - Linv*grad, optional clamp   (methodsIR_CuPy.py:463-468)
 // (x may alias g: every element is read before it is written)
-__global__ void k_fista_grad_step(const float *__restrict__ xt, const float *g, float *x,
-                                  size_t n, float linv, int nonneg) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    // separate multiply and subtract (two roundings) like the reference's two array ops
-    float v = __fsub_rn(xt[i], __fmul_rn(linv, g[i]));
-    if (nonneg) v = fmaxf(v, 0.f);
-    x[i] = v;
+__device__ __forceinline__ float grad_step1(float xt, float g, float linv, int nonneg) {
+  // separate multiply and subtract (two roundings) like the reference's two array ops
+  const float v = __fsub_rn(xt, __fmul_rn(linv, g));
+  return nonneg ? fmaxf(v, 0.f) : v;
+}
+__global__ void k_fista_grad_step(const float *__restrict__ xt, const float *g, float *x, size_t n, float linv,
+                                  int nonneg) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = grad_step1(xt[i], g[i], linv, nonneg);
+}
+// 128-bit variant (count % 4 == 0, 16-byte aligned arrays)
+__global__ void k_fista_grad_step4(const float4 *__restrict__ xt, const float4 *g, float4 *x, size_t n4, float linv,
+                                   int nonneg) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = xt[i], b = g[i];
+    x[i] = make_float4(grad_step1(a.x, b.x, linv, nonneg), grad_step1(a.y, b.y, linv, nonneg),
+                       grad_step1(a.z, b.z, linv, nonneg), grad_step1(a.w, b.w, linv, nonneg));
   }
 }
 
 // X_t = X + coef*(X - X_old)   (methodsIR_CuPy.py:475)
+__device__ __forceinline__ float momentum1(float a, float o, float coef) {
+  return __fadd_rn(a, __fmul_rn(coef, __fsub_rn(a, o)));
+}
 __global__ void k_fista_momentum(const float *__restrict__ x, const float *__restrict__ xo, float *__restrict__ xt,
                                  size_t n, float coef) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float a = x[i];
-    xt[i] = __fadd_rn(a, __fmul_rn(coef, __fsub_rn(a, xo[i])));
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    xt[i] = momentum1(x[i], xo[i], coef);
+}
+__global__ void k_fista_momentum4(const float4 *__restrict__ x, const float4 *__restrict__ xo,
+                                  float4 *__restrict__ xt, size_t n4, float coef) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = x[i], o = xo[i];
+    xt[i] = make_float4(momentum1(a.x, o.x, coef), momentum1(a.y, o.y, coef), momentum1(a.z, o.z, coef),
+                        momentum1(a.w, o.w, coef));
   }
 }
 
@@ -155,14 +178,24 @@ using namespace tmb;
 extern "C" int tmb_fista_grad_step(const float *x_t, const float *grad, float *x, size_t count, float l_inv,
                                    int nonneg, void *stream) {
   TMB_REQUIRE(x_t && grad && x, "tmb_fista_grad_step: null argument");
-  k_fista_grad_step<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(x_t, grad, x, count, l_inv, nonneg);
+  if (count % 4 == 0 && aligned16(x_t, grad, x))
+    k_fista_grad_step4<<<el_blocks(count / 4), EL_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(x_t), reinterpret_cast<const float4 *>(grad), reinterpret_cast<float4 *>(x),
+        count / 4, l_inv, nonneg);
+  else
+    k_fista_grad_step<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(x_t, grad, x, count, l_inv, nonneg);
   return check_launch("k_fista_grad_step");
 }
 
 extern "C" int tmb_fista_momentum(const float *x, const float *x_old, float *x_t, size_t count, float coef,
                                   void *stream) {
   TMB_REQUIRE(x && x_old && x_t, "tmb_fista_momentum: null argument");
-  k_fista_momentum<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(x, x_old, x_t, count, coef);
+  if (count % 4 == 0 && aligned16(x, x_old, x_t))
+    k_fista_momentum4<<<el_blocks(count / 4), EL_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(x_old), reinterpret_cast<float4 *>(x_t),
+        count / 4, coef);
+  else
+    k_fista_momentum<<<el_blocks(count), EL_THREADS, 0, (cudaStream_t)stream>>>(x, x_old, x_t, count, coef);
   return check_launch("k_fista_momentum");
 }
 

@@ -267,18 +267,27 @@ class RecToolsIRCuPy:
     def _prox_into(self, X: torch.Tensor, reg: dict, out: torch.Tensor) -> torch.Tensor:
         """``prox_regul`` (regularisersCuPy.py:6-38) writing into a preallocated volume."""
         dev = self.Atools.device_index
+        sh = self.zshard
+        sharded3d = sh is not None and sh.world > 1 and X.ndim == 3 and min(X.shape) > 1
         if "ROF_TV" in reg["method"]:
+            if sharded3d:
+                from tomobar_b200.zshard import ShardedROFTV
+
+                key = ("rof", tuple(X.shape), bool(reg.get("half_precision", False)))
+                if key not in self._sharded_tv:
+                    self._sharded_tv = {key: ShardedROFTV(sh, key[1], X.device, key[2])}
+                return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["time_marching_step"],
+                                             out=out)
             return ROF_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["time_marching_step"], dev,
                                reg.get("half_precision", False), out=out)
         if "PD_TV" in reg["method"]:
-            sh = self.zshard
-            if sh is not None and sh.world > 1 and X.ndim == 3 and min(X.shape) > 1:
+            if sharded3d:
                 # whole-volume 3-D TV across the z-shards: halo exchange between inner iterations
                 from tomobar_b200.zshard import ShardedPDTV
 
-                key = (tuple(X.shape), bool(reg.get("half_precision", False)))
+                key = ("pd", tuple(X.shape), bool(reg.get("half_precision", False)))
                 if key not in self._sharded_tv:
-                    self._sharded_tv = {key: ShardedPDTV(sh, key[0], X.device, key[1])}
+                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2])}
                 return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["methodTV"],
                                              self.nonneg_regul, reg["PD_LipschitzConstant"], out=out)
             return PD_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["methodTV"], self.nonneg_regul,

@@ -171,3 +171,46 @@ class ShardedPDTV:
             return res.clone()
         out.copy_(res)
         return out
+
+
+class ShardedROFTV:
+    """ROF_TV prox of a z-sharded 3-D volume, bit-identical to ``ROF_TV_cupy`` on the whole volume.
+
+    The normalised z difference of the plane below a shard enters the divergence at its first
+    plane (rudin_osher_fatemi_total_variation.cu:170-181, 235), and that difference itself needs
+    the plane below it: two ghost planes below, one above.  Per inner iteration each rank sends its
+    top two planes to the next rank and its bottom plane to the previous one."""
+
+    def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False):
+        nzl, ny, nx = shape
+        if nzl != shard.nz_local:
+            raise ValueError("ShardedROFTV: the volume shard does not match the z-partition")
+        if shard.world > 1 and nzl < 2:
+            raise ValueError("ShardedROFTV: every shard needs at least two slices")
+        self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
+        self.U = [torch.zeros((nzl + 3, ny, nx), dtype=torch.float32, device=device) for _ in range(2)]
+
+    def __call__(self, data: torch.Tensor, regularisation_parameter: float, iterations: int,
+                 time_marching_parameter: float = 0.001, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from tomobar_b200._lib import lib, check
+        from tomobar_b200._tensors import ptr, stream_ptr
+
+        sh = self.shard
+        nzl, ny, nx = self.shape
+        if tuple(data.shape) != self.shape or data.dtype != torch.float32 or not data.is_contiguous():
+            raise ValueError(f"ShardedROFTV: expected a contiguous float32 volume shard of shape {self.shape}")
+        U = self.U
+        U[0][2:nzl + 2].copy_(data)
+        ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
+        with torch.cuda.device(self.device):
+            for it in range(int(iterations)):
+                a, b = it % 2, 1 - it % 2
+                sh.exchange_halos([(U[a][nzl:nzl + 2], U[a][0:2])], [(U[a][2], U[a][nzl + 2])])
+                check(lib.tmb_rof_tv_iter(ptr(data), ptr(U[a][2:]), ptr(U[b][2:]), nzl, ny, nx,
+                                          float(regularisation_parameter), float(time_marching_parameter),
+                                          int(self.half), ghost_lo, ghost_hi, stream_ptr(data)), "tmb_rof_tv_iter")
+        res = U[int(iterations) % 2][2:nzl + 2]
+        if out is None:
+            return res.clone()
+        out.copy_(res)
+        return out
