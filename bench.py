@@ -204,9 +204,14 @@ def run_reference_arm(args, cfg):
 
 
 def _config(cfg, gpus):
+    if cfg.get("algo") == "admm":
+        workload = (f"ADMM-OS + ROF_TV, volume {cfg['n']}x{cfg['n']}x{cfg['nz']}, {cfg['na']} angles, "
+                    f"OS={cfg['os']}, rho 1, alpha 1.7, ROF_TV 30 inner iterations")
+    else:
+        workload = (f"FISTA-OS + PD_TV, volume {cfg['n']}x{cfg['n']}x{cfg['nz']}, {cfg['na']} angles, "
+                    f"OS={cfg['os']}, PD_TV {cfg['tv_iters']} inner iterations (fp32 duals)")
     return {
-        "workload": (f"FISTA-OS + PD_TV, volume {cfg['n']}x{cfg['n']}x{cfg['nz']}, {cfg['na']} angles, "
-                     f"OS={cfg['os']}, PD_TV {cfg['tv_iters']} inner iterations (fp32 duals)"),
+        "workload": workload,
         "n": cfg["n"], "nz": cfg["nz"], "angles": cfg["na"], "os_number": cfg["os"],
         "tv_inner_iterations": cfg["tv_iters"], "z_shards": gpus,
         "tv_across_shards": "halo exchange (exact)" if gpus > 1 else "n/a",
@@ -231,11 +236,14 @@ def main():
     ap.add_argument("--half", action="store_true", help="fp16 storage of the TV dual variables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--algo", default="fista", choices=["fista", "admm"],
+                    help="fista: FISTA-OS + PD_TV (the headline metric); admm: ADMM-OS + ROF_TV (BASELINE.json "
+                         "config 3: rho 1, alpha 1.7, 30 inner iterations), reported under its own metric name")
     ap.add_argument("--independent-tv", action="store_true",
                     help="multi-GPU: TV per z-shard without halo exchange (seams at the shard borders)")
     args = ap.parse_args()
     cfg = dict(n=args.n, nz=args.nz, na=args.angles, os=args.os, tv_iters=args.tv_iters,
-               tv_lambda=HEADLINE["tv_lambda"])
+               tv_lambda=HEADLINE["tv_lambda"], algo=args.algo)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -291,8 +299,27 @@ def main():
     L_inv = 1.0 / 2.0e4  # fixed step: the benchmark times the loop, not the power method
     state = {"t": np.float32(1.0), "sub": 0}
 
+    admm = args.algo == "admm"
+    if admm:
+        # ADMM state (methodsIR_CuPy.py:531-566): x, z, z_old, u; G doubles as the prox input
+        reg = {"method": "ROF_TV", "regul_param": cfg["tv_lambda"], "iterations": 30, "time_marching_step": 1e-3,
+               "half_precision": bool(args.half)}
+        Zv, Zo, Uv = torch.zeros(vol_shape, device=dev), torch.zeros(vol_shape, device=dev), X_old
+        tau_admm, rho = 0.9 / (2.0e4 + 1.0), 1.0
+
+    def substep_admm():
+        A.grad_data_term(Zv, b, state["sub"], "LS", None, out=G)
+        check(lib.tmb_admm_z_step(ptr(Zv), ptr(Zo), ptr(X), ptr(Uv), ptr(G), ptr(X_t), count, tau_admm, rho, 1, 1,
+                                  1.7, st), "admm_z")
+        rec._prox_into(X_t, reg, X)
+        state["sub"] = (state["sub"] + 1) % os_n
+        if state["sub"] == 0:
+            check(lib.tmb_admm_u_step(ptr(Uv), ptr(Zv), ptr(X), count, st), "admm_u")
+
     def substep():
         nonlocal X, X_old
+        if admm:
+            return substep_admm()
         X_old, X = X, X_old
         t_old = state["t"]
         A.grad_data_term(X_t, b, state["sub"], "LS", None, out=G)
@@ -310,7 +337,7 @@ def main():
         torch.cuda.synchronize()
 
     # our kernels per sub-step: layout conversion, k_fp, k_bp, gradient step, PD_TV iterations, momentum
-    launches_per_step = 1 + 1 + 1 + 1 + cfg["tv_iters"] + 1
+    launches_per_step = 1 + 1 + 1 + 1 + (30 if args.algo == "admm" else cfg["tv_iters"]) + 1
 
     for _ in range(args.warmup):
         substep()
@@ -351,15 +378,22 @@ def main():
     ms_fp = timed(lambda: check(lib.tmb_fp3d(A._g, 0, ptr(X_t), ptr(sub_sino), ptr(A._workspace()), st), "fp"), 3)
     ms_bp = timed(lambda: check(lib.tmb_bp3d(A._g, 0, ptr(sub_sino), ptr(G), ptr(A._workspace()), st), "bp"), 3)
     tv_reps = max(4, cfg["tv_iters"])
-    ms_tv = timed(lambda: PD_TV_cupy(G, reg["regul_param"], tv_reps, 0, 1, 12.0, local_rank,
-                                     reg["half_precision"], out=X), 2) / tv_reps
+    if admm:
+        from tomobar_b200.regularisersCuPy import ROF_TV_cupy
+
+        ms_tv = timed(lambda: ROF_TV_cupy(G, reg["regul_param"], tv_reps, 1e-3, local_rank, reg["half_precision"],
+                                          out=X), 2) / tv_reps
+    else:
+        ms_tv = timed(lambda: PD_TV_cupy(G, reg["regul_param"], tv_reps, 0, 1, 12.0, local_rank,
+                                         reg["half_precision"], out=X), 2) / tv_reps
     upd_sub = float(nz_loc) * n * n * na_s
-    bytes_tv = (24.0 if args.half else 36.0) * count
+    bytes_tv = (12.0 if admm else (24.0 if args.half else 36.0)) * count
     peak, peak_src = measured_peak_hbm()
     tv_gbs = bytes_tv / (ms_tv * 1e-3) / 1e9
-    share_tv = ms_tv * cfg["tv_iters"] / ms_step
+    share_tv = ms_tv * (30 if admm else cfg["tv_iters"]) / ms_step
     roofline = {
-        "kernel": "k_pd_tv3d_w (one Chambolle-Pock iteration, warp-strip kernel)", "bound": "hbm", "achieved": tv_gbs, "peak": peak,
+        "kernel": ("k_rof_tv3d_w (one fused ROF iteration; instruction-bound, 12 B/voxel)" if admm else
+                   "k_pd_tv3d_w (one Chambolle-Pock iteration, warp-strip kernel)"), "bound": "hbm", "achieved": tv_gbs, "peak": peak,
         "unit": "GB/s", "frac": tv_gbs / peak, "peak_source": peak_src, "traffic": None,
         "algorithmic_bytes_per_launch": bytes_tv, "ms_per_launch": ms_tv, "share_of_step": share_tv,
     }
@@ -383,9 +417,10 @@ def main():
 
         def e2e_iter():
             d = b_host.to(dev, non_blocking=True)
-            r = rec.FISTA({"projection_data": d},
-                          {"iterations": 1, "lipschitz_const": 2.0e4, "nonnegativity": True,
-                           "recon_mask_radius": None}, dict(reg))
+            alg = {"iterations": 1, "lipschitz_const": 2.0e4, "nonnegativity": True, "recon_mask_radius": None}
+            if admm:
+                alg.update({"ADMM_rho_const": 1.0, "ADMM_relax_par": 1.7})
+            r = (rec.ADMM if admm else rec.FISTA)({"projection_data": d}, alg, dict(reg))
             out_host.copy_(r, non_blocking=True)  # every rank returns its own z-block to the host
 
         e2e_iter()
@@ -411,7 +446,8 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if not admm else "admm_os_iterations_per_sec", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(cfg, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

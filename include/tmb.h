@@ -60,6 +60,11 @@ int tmb_geom_table(const tmb_geom *g, float *out);
  * zero-fills it ONCE (the kernels keep the zero borders intact) and passes it to every call. */
 size_t tmb_geom_workspace_bytes(const tmb_geom *g);
 
+/* Debug/test switch read by tmb_geom_create: 0 = choose the forward-projector kernel by stack height
+ * (k_fpq with the 32-slice-blocked layouts from 17 slices up, else k_fp), 1 = k_fp, 2 = k_fpq.
+ * Returns the old value. */
+int tmb_fp_set_kernel(int mode);
+
 /* ---- projector pair --------------------------------------------------------------------
  * tmb_fp3d replaces AstraBase.runAstraProj3DCuPy -> astra direct_FP3D (astra_base.py:560-606)
  *          i.e. AstraTools3D._forwprojCuPy/_forwprojOSCuPy (astra_tools3d.py:78-86)

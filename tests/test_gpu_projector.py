@@ -21,6 +21,8 @@ CASES = [
     (16, 160, 160, 180, 0.0, None),
     (9, 50, 70, 37, 0.5, 5),
     (8, 200, 260, 90, 3.0, 6),
+    (33, 70, 100, 40, 0.75, 4),   # > 16 slices: the 32-slice-blocked forward projector (k_fpq)
+    (40, 96, 64, 24, 0.0, None),
 ]
 
 
@@ -152,3 +154,28 @@ def test_linearity_and_zero_at_scale():
     lhs = torch.sum(ax.double() * q.double()).item()
     rhs = torch.sum(x.double() * full._backprojCuPy(q).double()).item()
     assert abs(lhs - rhs) / max(abs(lhs), abs(rhs)) < 5e-2
+
+
+@pytest.mark.parametrize("nz,n,nu,na,os_n", [(5, 64, 80, 36, 3), (20, 130, 130, 50, None), (70, 48, 40, 21, 2)])
+def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
+    """k_fp (8 slices per thread) and k_fpq (bank-conflict-free 32-slice blocks) share their
+    arithmetic: plain projection and the fused gradient are bit-identical."""
+    from tomobar_b200._lib import lib
+    from tomobar_b200.projector import ProjTools3D
+
+    g = torch.Generator(device="cuda").manual_seed(nz)
+    vol = torch.randn((nz, n, n), device="cuda", generator=g)
+    b = torch.randn((nz, na, nu), device="cuda", generator=g)
+    w = torch.rand((nz, na, nu), device="cuda", generator=g)
+    res = {}
+    for mode in (1, 2):
+        old = lib.tmb_fp_set_kernel(mode)
+        try:
+            P = ProjTools3D(nu, 0, nz, _angles(na), 0.5, n, "gpu", 0, os_n)
+        finally:
+            lib.tmb_fp_set_kernel(old)
+        sub = None if os_n is None else os_n - 1
+        fp = P._forwprojCuPy(vol) if os_n is None else P._forwprojOSCuPy(vol, sub)
+        res[mode] = (fp, P.grad_data_term(vol, b, sub, "PWLS", w), P.grad_data_term(vol, b.abs(), sub, "KL"))
+    for a, c in zip(res[1], res[2]):
+        assert torch.equal(a, c)

@@ -30,6 +30,7 @@ SIGNATURES = {
     "tmb_geom_subset_row": (_i, [_vp, _i, _ip]),
     "tmb_geom_table": (_i, [_vp, C.POINTER(C.c_float)]),
     "tmb_geom_workspace_bytes": (_sz, [_vp]),
+    "tmb_fp_set_kernel": (_i, [_i]),
     "tmb_fp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_bp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_grad": (_i, [_vp, _i, _i, _fp, _fp, _fp, _fp, _vp, _vp]),

@@ -11,11 +11,19 @@ static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int subset_size(const tmb_geom *g, int subset);
 static std::atomic<uint64_t> g_next_id{1};
+// test hook: which forward-projector kernel geometries created from now on use
+// (0 = by stack height, 1 = k_fp, 2 = k_fpq)
+static int g_fp_kernel = 0;
 }  // namespace tmb
 
 using namespace tmb;
 
 extern "C" int tmb_version(void) { return 100; }
+extern "C" int tmb_fp_set_kernel(int mode) {
+  const int old = g_fp_kernel;
+  g_fp_kernel = (mode == 1 || mode == 2) ? mode : 0;
+  return old;
+}
 extern "C" const char *tmb_last_error(void) { return g_err.c_str(); }
 
 // Per-angle fp32 table derived in double from the parallel3d_vec vectors of
@@ -62,7 +70,11 @@ extern "C" tmb_geom *tmb_geom_create(int nz, int n, int nu, int na, const double
   g->table = static_cast<float *>(std::malloc(sizeof(float) * 8 * (size_t)na));
   fill_table(g->table, n, nu, na, cos_t, sin_t, cor);
   g->id = g_next_id.fetch_add(1);
-  const size_t vbytes = sizeof(float4) * (size_t)g->d.nzc * n * g->d.qp;
+  g->d.nzg = (nz + ZC * FQ_CG - 1) / (ZC * FQ_CG);
+  g->d.qpq = n + 2 * QPAD;
+  g->fp_q = g_fp_kernel == 1 ? 0 : (g_fp_kernel == 2 ? 1 : (nz >= FQ_MIN_NZ ? 1 : 0));
+  const size_t vbytes = g->fp_q ? sizeof(float4) * FQ_CG * (size_t)g->d.nzg * n * g->d.qpq
+                                : sizeof(float4) * (size_t)g->d.nzc * n * g->d.qp;
   const size_t sbytes = sizeof(float4) * (size_t)g->d.nzc * na * g->d.up;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   g->off_v0 = 0;

@@ -54,6 +54,16 @@ constexpr int FP_W = 184;     // volume-line window of FP_K bins: ceil(127*sqrt(
 constexpr int VPAD = FP_W;    // zero border of V0 / V1
 constexpr int MAX_ANGLES = 2000;  // constant-memory table capacity (2 x float4 per angle)
 
+// "Q" layouts of the forward projector for volumes of more than FQ_MIN_NZ slices: z is blocked in
+// groups of 32 slices that sit next to each other per in-plane position (128 B = one shared-memory
+// wavefront), so the 8 lanes of a quarter-warp read 8 z-chunks of ONE position: bank-conflict free
+//   VQ1[zg][r][QPAD + c + QPAD][8][4]   VQ0[zg][c][QPAD + r + QPAD][8][4]
+constexpr int FQ_K = 64;          // detector bins per CTA
+constexpr int FQ_CG = 8;          // z-chunks (of 4 slices) per position
+constexpr int FQ_W = 96;          // volume-line window of FQ_K bins: ceil(63*sqrt(2)) + 4, rounded up
+constexpr int QPAD = FQ_W;        // zero border
+constexpr int FQ_MIN_NZ = 17;     // smaller stacks keep the 8-slice kernel
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct GeomDims {
@@ -61,6 +71,8 @@ struct GeomDims {
   int nzc;   // z-chunks allocated (multiple of NZC)
   int up;    // nu + 2*SPAD
   int qp;    // n + 2*VPAD
+  int nzg;   // 32-slice groups of the Q layouts
+  int qpq;   // n + 2*QPAD
 };
 
 #ifdef __CUDACC__
@@ -122,6 +134,7 @@ struct tmb_geom {
   int bins;                 // ceil(na / os)
   float *table;             // host [na][8]
   uint64_t id;              // identity for the constant-memory cache
+  int fp_q;                 // 1: forward projector runs on the Q layouts (k_fpq), 0: k_fp
   // workspace carve-up (bytes offsets)
   size_t off_v0, off_v1, off_s, ws_bytes;
 };

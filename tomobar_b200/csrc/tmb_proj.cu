@@ -269,6 +269,7 @@ struct FpArgs {
   const float *b;    // mode 1: full data sinogram [nz][na_tot][nu]
   const float *w;    // mode 1: PWLS weights (same layout) or nullptr
   int n, nu, up, qp, nz, na_loc, na_tot;
+  int nzc_alloc;          // z-chunks S_int holds (k_fpq's 32-slice groups may reach past it)
   int a_first, a_stride;  // constant-table slot of local angle j
   int g_first, g_stride;  // global angle index (row of b / w) of local angle j
   int j_begin;            // local angle of blockIdx.y == 0
@@ -407,6 +408,185 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
 }
 
 // ==========================================================================================
+// forward projection on the Q layouts (stacks of >= FQ_MIN_NZ slices)
+//
+// Same Joseph march as k_fp, re-mapped so that the shared-memory reads are bank-conflict free:
+// a thread owns ONE detector bin and ONE z-chunk (4 slices); the 8 lanes of a quarter-warp are
+// the 8 z-chunks of one bin, and the Q layouts keep those 8 chunks next to each other (128 B per
+// in-plane position), so every LDS.128 wavefront is one contiguous 128-byte row.  (In k_fp a
+// quarter-warp is 8 consecutive bins whose positions span up to 11 elements at 45 degrees: 32 % of
+// its wavefronts are bank conflicts.)  CTA = FQ_K bins x 32 slices = 512 consumer threads + one
+// producer warp that streams FQ_G lines per stage with one bulk copy (TMA) per line.
+// ==========================================================================================
+constexpr int FQ_G = 3;       // volume lines per pipeline stage
+constexpr int FQ_STAGES = 3;
+constexpr int FQ_THREADS = FQ_K * FQ_CG;
+
+// vol[nz][n][n] -> VQ1 / VQ0; a block converts a 32 x 32 in-plane tile of 8 slices (2 chunks)
+__global__ void k_vol_to_intq(const float *__restrict__ vol, float4 *__restrict__ v0, float4 *__restrict__ v1, int nz,
+                              int n, int qpq) {
+  __shared__ float4 tile[2][32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int zc0 = blockIdx.z * 2;  // first of the block's two z-chunks
+  const int zg = zc0 / FQ_CG, cc = zc0 % FQ_CG;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    float v[2 * ZC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < n && c < n) {
+#pragma unroll
+      for (int k = 0; k < 2 * ZC; ++k) {
+        const int z = zc0 * ZC + k;
+        if (z < nz) v[k] = vol[((size_t)z * n + r) * n + c];
+      }
+    }
+    const float4 q0 = make_float4(v[0], v[1], v[2], v[3]), q1 = make_float4(v[4], v[5], v[6], v[7]);
+    tile[0][j][tx] = q0;
+    tile[1][j][tx] = q1;
+    if (r < n && c < n) {
+      float4 *d = v1 + (((size_t)zg * n + r) * qpq + QPAD + c) * FQ_CG + cc;
+      d[0] = q0;
+      d[1] = q1;
+    }
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < n && c < n) {
+      float4 *d = v0 + (((size_t)zg * n + c) * qpq + QPAD + r) * FQ_CG + cc;
+      d[0] = tile[0][tx][j];
+      d[1] = tile[1][tx][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
+  extern __shared__ __align__(128) unsigned char fp_smem[];
+  // buf[stage][line][position][chunk]
+  float4(*buf)[FQ_G][FQ_W][FQ_CG] = reinterpret_cast<float4(*)[FQ_G][FQ_W][FQ_CG]>(fp_smem);
+  __shared__ int wst[FQ_STAGES][FQ_G];
+  __shared__ __align__(8) uint64_t full_bar[FQ_STAGES], empty_bar[FQ_STAGES];
+
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * FQ_K;
+  const int j = p.j_begin + blockIdx.y;  // local angle
+  const int zg = blockIdx.z;
+  const float4 t = c_fp[p.a_first + j * p.a_stride];
+  const float alpha = t.x, b0 = t.y, bstep = t.z;
+  const float scale = fabsf(t.w);
+  const float4 *vsrc = (t.w < 0.f) ? p.v0 : p.v1;
+  const float half = 0.5f * (float)p.n;
+
+  if (tid == 0) {
+    for (int s = 0; s < FQ_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], FQ_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int n_iter = (p.n + FQ_G - 1) / FQ_G;
+  const int win = min(FQ_W, (int)ceilf((float)(FQ_K - 1) * fabsf(bstep)) + 4);
+
+  if (tid >= FQ_THREADS) {
+    if (tid == FQ_THREADS) {
+      const float beta_a = fmaf((float)k0, bstep, b0);
+      const float beta_b = fmaf((float)(k0 + FQ_K - 1), bstep, b0);
+      const float beta_min = fminf(beta_a, beta_b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % FQ_STAGES;
+        const uint32_t ph = (it / FQ_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int m0 = it * FQ_G;
+        const int ng = min(FQ_G, p.n - m0);
+        for (int gm = 0; gm < ng; ++gm) {
+          const float xm = (float)(m0 + gm) - half + 0.5f;
+          int ws = (int)floorf(fmaf(alpha, xm, beta_min)) - 1;
+          ws = max(-QPAD, min(ws, p.n));
+          wst[s][gm] = ws;
+        }
+        // the arrive releases the window starts to the consumers that acquire the completed phase
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * win * FQ_CG * sizeof(float4)));
+        for (int gm = 0; gm < ng; ++gm) {
+          const float4 *src = vsrc + (((size_t)zg * p.n + (m0 + gm)) * p.qp + (QPAD + wst[s][gm])) * FQ_CG;
+          bulk_g2s(&buf[s][gm][0][0], src, (uint32_t)(win * FQ_CG * sizeof(float4)), &full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  const int lane = tid & 31;
+  const int cc = tid & (FQ_CG - 1);  // z-chunk inside the group
+  const int k = k0 + (tid >> 3);     // detector bin
+  const float beta = fmaf((float)k, bstep, b0);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const bool quant = p.quant != 0;
+  for (int it = 0; it < n_iter; ++it) {
+    const int s = it % FQ_STAGES;
+    const uint32_t ph = (it / FQ_STAGES) & 1;
+    mbar_wait(&full_bar[s], ph);
+    const int m0 = it * FQ_G;
+    const int ng = min(FQ_G, p.n - m0);
+    // (float)(m0 + gm) - half + 0.5f: integers and halves below 2^24 are exact, so base + gm is identical
+    const float xbase = (float)m0 - half + 0.5f;
+    const float4 *sbuf = &buf[s][0][0][cc];
+#pragma unroll
+    for (int gm = 0; gm < FQ_G; ++gm) {
+      if (gm < ng) {
+        const float rho = fmaf(alpha, xbase + (float)gm, beta);
+        // floor and round-to-nearest-even without the quarter-rate conversion pipe: one F2I, the
+        // rest are adds (|rho| < 2^22; f * 256 in [0, 256])
+        const int ifl = __float2int_rd(rho);
+        float f = rho - (float)ifl;
+        if (quant) f = ((f * 256.0f + 12582912.0f) - 12582912.0f) * (1.0f / 256.0f);
+        const float g = 1.0f - f;
+        const int i = max(0, min(ifl - wst[s][gm], win - 2));
+        const float4 *q = sbuf + (gm * FQ_W + i) * FQ_CG;
+        lerp_acc(acc, g, f, q[0], q[FQ_CG]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  if (k >= p.nu) return;
+  const int zc = zg * FQ_CG + cc;
+  float *a4 = reinterpret_cast<float *>(&acc);
+  if (p.mode == 0) {
+#pragma unroll
+    for (int q = 0; q < ZC; ++q) {
+      const int z = zc * ZC + q;
+      if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[q], scale);
+    }
+  } else {
+    // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
+    if (zc * ZC >= p.nzc_alloc * ZC) return;
+    const int ga = p.g_first + j * p.g_stride;
+    float r[ZC];
+#pragma unroll
+    for (int q = 0; q < ZC; ++q) {
+      const int z = zc * ZC + q;
+      float v = 0.f;
+      if (z < p.nz) {
+        const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
+        const float ax = __fmul_rn(a4[q], scale);
+        if (p.fidelity == TMB_FID_KL) {
+          v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
+        } else {
+          v = __fsub_rn(ax, p.b[idx]);
+          if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
+        }
+      }
+      r[q] = v;
+    }
+    p.sint[((size_t)zc * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ==========================================================================================
 // residual post-pass for the robust / ring-artefact data terms (extension, see DESIGN.md: the
 // reference snapshot only keeps their call sites, Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:
 // 197,307-309).  Runs on the residual the forward projector's epilogue left in S_int, one thread
@@ -507,6 +687,11 @@ static int launch_sino_to_int(const tmb_geom *g, const float *sino, float4 *sint
 }
 
 static int launch_vol_to_int(const tmb_geom *g, const float *vol, float4 *v0, float4 *v1, cudaStream_t st) {
+  if (g->fp_q) {
+    dim3 gridq((g->d.n + 31) / 32, (g->d.n + 31) / 32, g->d.nzg * FQ_CG / 2);
+    k_vol_to_intq<<<gridq, dim3(32, 8), 0, st>>>(vol, v0, v1, g->d.nz, g->d.n, g->d.qpq);
+    return check_launch("k_vol_to_intq");
+  }
   dim3 grid((g->d.n + 31) / 32, (g->d.n + 31) / 32, g->d.nzc);
   k_vol_to_int<<<grid, dim3(32, 8), 0, st>>>(vol, v0, v1, g->d.nz, g->d.n, g->d.qp, 1, 1);
   return check_launch("k_vol_to_int");
@@ -548,14 +733,18 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
   const int first = subset_first(g, subset), stride = subset_stride(g, subset);
   FpArgs a;
   a.v0 = v0; a.v1 = v1; a.sino = sino; a.sint = sint; a.b = b; a.w = w;
-  a.n = g->d.n; a.nu = g->d.nu; a.up = g->d.up; a.qp = g->d.qp; a.nz = g->d.nz;
-  a.na_loc = na_loc; a.na_tot = g->d.na;
+  a.n = g->d.n; a.nu = g->d.nu; a.up = g->d.up; a.qp = g->fp_q ? g->d.qpq : g->d.qp; a.nz = g->d.nz;
+  a.na_loc = na_loc; a.na_tot = g->d.na; a.nzc_alloc = g->d.nzc;
   a.g_first = first; a.g_stride = stride;
   a.mode = mode; a.fidelity = fidelity; a.quant = g->quant8;
-  const size_t smem = sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W;
+  const size_t smem = g->fp_q ? sizeof(float4) * FQ_STAGES * FQ_G * FQ_W * FQ_CG
+                              : sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W;
   static bool attr_set = false;
   if (!attr_set) {
-    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W)));
+    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fpq, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(float4) * FQ_STAGES * FQ_G * FQ_W * FQ_CG)));
     attr_set = true;
   }
   int j = 0;
@@ -569,8 +758,13 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
     a.a_first = gl - chunk_base - j * stride; a.a_stride = stride;
     a.j_begin = j;
     // grid.y is limited to 65535: far above any angle count
-    dim3 grid((g->d.nu + FP_K - 1) / FP_K, cnt, g->d.nzc / NZC);
-    k_fp<<<grid, FP_K + 32, smem, st>>>(a);
+    if (g->fp_q) {
+      dim3 gridq((g->d.nu + FQ_K - 1) / FQ_K, cnt, g->d.nzg);
+      k_fpq<<<gridq, FQ_THREADS + 32, smem, st>>>(a);
+    } else {
+      dim3 grid((g->d.nu + FP_K - 1) / FP_K, cnt, g->d.nzc / NZC);
+      k_fp<<<grid, FP_K + 32, smem, st>>>(a);
+    }
     rc = check_launch("k_fp");
     if (rc) return rc;
     j += cnt;
