@@ -214,7 +214,7 @@ def _config(cfg, gpus):
         "workload": workload,
         "n": cfg["n"], "nz": cfg["nz"], "angles": cfg["na"], "os_number": cfg["os"],
         "tv_inner_iterations": cfg["tv_iters"], "z_shards": gpus,
-        "tv_across_shards": "halo exchange (exact)" if gpus > 1 else "n/a",
+        "tv_across_shards": cfg.get("halo", "n/a") if gpus > 1 else "n/a",
         "l2_policy": "working set per step (>= 8 GB per rank) far exceeds the 126 MB L2; no flush needed",
     }
 
@@ -239,11 +239,17 @@ def main():
     ap.add_argument("--algo", default="fista", choices=["fista", "admm"],
                     help="fista: FISTA-OS + PD_TV (the headline metric); admm: ADMM-OS + ROF_TV (BASELINE.json "
                          "config 3: rho 1, alpha 1.7, 30 inner iterations), reported under its own metric name")
+    ap.add_argument("--halo-messages", action="store_true",
+                    help="multi-GPU: refresh the TV ghost planes with NCCL send/recv instead of letting the "
+                         "kernel read the neighbours' planes over NVLink (peer memory)")
     ap.add_argument("--independent-tv", action="store_true",
                     help="multi-GPU: TV per z-shard without halo exchange (seams at the shard borders)")
     args = ap.parse_args()
     cfg = dict(n=args.n, nz=args.nz, na=args.angles, os=args.os, tv_iters=args.tv_iters,
-               tv_lambda=HEADLINE["tv_lambda"], algo=args.algo)
+               tv_lambda=HEADLINE["tv_lambda"], algo=args.algo,
+               halo=("independent z-blocks" if args.independent_tv else
+                     "exact, NCCL messages between inner iterations" if args.halo_messages else
+                     "exact, peer loads over NVLink inside the TV kernel"))
     if args.warmup < 3:
         args.warmup = 3
 
@@ -278,6 +284,7 @@ def main():
     rec = RecToolsIRCuPy(n, 0, nz_loc, 0.0, angles, n, local_rank, os_n)
     if world > 1 and not args.independent_tv:
         rec.set_zshard(shard)
+        rec.tv_peer_memory = False if args.halo_messages else None
     rec.nonneg_regul = 1
     A = rec.Atools
     # synthetic data generated on the device, slice blocks of 16 to bound temporaries

@@ -116,11 +116,16 @@ int tmb_rof_tv(const float *in, float *out, int dz, int dy, int dx, float regula
  * plane dz of u_in must exist (the next shard's first plane); with ghost_lo plane -1 of u_in and of
  * p1_in..p3_in must exist (the previous shard's last plane).  The caller refreshes those ghost planes
  * between iterations; the sharded result is then bit-identical to the whole-volume one.
+ * u_lo / p*_lo / u_hi name the ghost planes explicitly (NULL = the memory adjacent to the arrays as
+ * described above).  They may be PEER pointers into the neighbouring GPU's own buffers (NVLink /
+ * NVSwitch P2P mapping, e.g. torch symmetric memory): the kernel then pulls its halos itself and the
+ * caller only places a cross-GPU barrier between iterations.
  * Ghost planes need dx % 4 == 0 and 16-byte aligned arrays (TMB_ERR_UNSUPPORTED otherwise).       */
 int tmb_pd_tv_iter(const float *in, const float *u_in, float *u_out, const void *p1_in, const void *p2_in,
                    const void *p3_in, void *p1_out, void *p2_out, void *p3_out, int dz, int dy, int dx,
                    float regularisation_parameter, int methodTV, int nonneg, float lipschitz_const,
-                   int half_precision, int ghost_lo, int ghost_hi, void *stream);
+                   int half_precision, int ghost_lo, int ghost_hi, const float *u_lo, const void *p1_lo,
+                   const void *p2_lo, const void *p3_lo, const float *u_hi, void *stream);
 
 /* One ROF iteration on caller-owned ping-pong buffers (rudin_osher_fatemi_total_variation.cu:157-248,
  * both kernels fused; regularisersCuPy.py:112-162 launches them per iteration).  z-SHARDS: with
@@ -128,7 +133,8 @@ int tmb_pd_tv_iter(const float *in, const float *u_in, float *u_out, const void 
  * difference of plane -1 enters the divergence at plane 0).  Needs dx % 4 == 0 and aligned arrays. */
 int tmb_rof_tv_iter(const float *in, const float *u_in, float *u_out, int dz, int dy, int dx,
                     float regularisation_parameter, float time_marching_parameter, int half_precision,
-                    int ghost_lo, int ghost_hi, void *stream);
+                    int ghost_lo, int ghost_hi, const float *u_lo /* planes -2,-1 */, const float *u_hi,
+                    void *stream);
 
 /* Debug/test switch: 1 routes 3-D TV through the simple one-thread-per-voxel kernels instead of
  * the z-marching ones, 2 through the CTA-tiled z-marching kernels, 3 / 4 force the register-fed / TMA-fed

@@ -65,3 +65,19 @@ def test_normaliser_matches_numpy_restatement(scan_all):
     # no log
     lin = normaliser(data, flats, darks, log=False).cpu().numpy()
     assert lin.min() >= 0.0
+
+
+@pytest.mark.parametrize("method", ["mean", "median"])
+def test_normaliser_range(scan_all, method):  # reference tests/test_tools.py:9-15, 27-35
+    if "raw" not in scan_all:
+        pytest.skip("tests/golden/tomo_standard.npz missing")
+    from tomobar_b200.supp.suppTools import _apply_horiz_detector_padding, normaliser
+
+    data, flats, darks = (np.float32(a) for a in scan_all["raw"])
+    out = normaliser(data, flats, darks, method=method)
+    assert 2 <= float(out.max()) <= 3 and tuple(out.shape) == (180, 128, 160) and out.dtype == torch.float32
+    out1 = normaliser(data.swapaxes(0, 1).copy(), flats.swapaxes(0, 1).copy(), darks.swapaxes(0, 1).copy(), axis=1)
+    assert 2 <= float(out1.max()) <= 3 and tuple(out1.shape) == (128, 180, 160)
+    padded = _apply_horiz_detector_padding(out1, 15, True)  # :18-24
+    assert tuple(padded.shape) == (128, 180, 190)
+    assert torch.equal(padded[..., :15], out1[..., :1].expand(-1, -1, 15))

@@ -31,15 +31,18 @@ def _worker(rank, world, init_file, results):
         full = full.to(dev)
         out = {}
         # --- sharded PD_TV prox == whole-volume prox, bit for bit --------------------------------
-        for half in (False, True):
-            tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half)
-            part = tv(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0)
-            whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
-            gathered = sh.all_gather_volume(part)
-            out[f"tv_equal_half{int(half)}"] = bool(torch.equal(gathered, whole))
-        rof = ShardedROFTV(sh, (sh.nz_local, n, n), dev, False)
-        part = rof(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 1e-3)
-        out["rof_equal"] = bool(torch.equal(sh.all_gather_volume(part), ROF_TV_cupy(full, 4e-4, 9, 1e-3, rank, False)))
+        out["tv_equal_half0"] = out["tv_equal_half1"] = out["rof_equal"] = True
+        for peer in (True, False):  # halos read over NVLink inside the kernel / sent as messages
+            for half in (False, True):
+                tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half, peer_memory=peer)
+                whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
+                for _ in range(2):  # buffers are reused across calls
+                    part = tv(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0)
+                    out[f"tv_equal_half{int(half)}"] &= bool(torch.equal(sh.all_gather_volume(part), whole))
+            rof = ShardedROFTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=peer)
+            part = rof(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 1e-3)
+            out["rof_equal"] &= bool(torch.equal(sh.all_gather_volume(part),
+                                                 ROF_TV_cupy(full, 4e-4, 9, 1e-3, rank, False)))
         # --- sharded FISTA-OS + PD_TV == whole-volume run ------------------------------------------
         angles = np.linspace(0, np.pi, na, endpoint=False).astype(np.float32)
         sino = torch.rand((nz, na, n), generator=g).to(dev)

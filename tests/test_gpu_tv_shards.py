@@ -45,7 +45,8 @@ def _sharded_prox(v, cuts, lam, iters, methodTV, nonneg, lip, half):
             check(lib.tmb_pd_tv_iter(ptr(s["data"]), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
                                      ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
                                      nzl, ny, nx, lam, methodTV, nonneg, lip, int(half), int(i > 0),
-                                     int(i + 1 < len(S)), stream_ptr(v)), "tmb_pd_tv_iter")
+                                     int(i + 1 < len(S)), None, None, None, None, None, stream_ptr(v)),
+                  "tmb_pd_tv_iter")
     return torch.cat([s["U"][iters % 2][1:s["nzl"] + 1] for s in S], dim=0)
 
 
@@ -89,7 +90,7 @@ def _sharded_rof(v, cuts, lam, iters, tau, half):
         for i, s in enumerate(S):
             U, nzl = s["U"], s["nzl"]
             check(lib.tmb_rof_tv_iter(ptr(s["data"]), ptr(U[a][2:]), ptr(U[b][2:]), nzl, ny, nx, lam, tau, int(half),
-                                      int(i > 0), int(i + 1 < len(S)), stream_ptr(v)), "tmb_rof_tv_iter")
+                                      int(i > 0), int(i + 1 < len(S)), None, None, stream_ptr(v)), "tmb_rof_tv_iter")
     return torch.cat([s["U"][iters % 2][2:s["nzl"] + 2] for s in S], dim=0)
 
 
@@ -114,5 +115,53 @@ def test_ghost_planes_need_the_strip_kernel():
     U = torch.zeros((8, 10, 30), device="cuda")
     P = [torch.zeros((7, 10, 30), device="cuda") for _ in range(6)]
     rc = lib.tmb_pd_tv_iter(ptr(v), ptr(U[1:]), ptr(torch.zeros_like(U)[1:]), *[ptr(p[1:]) for p in P], 6, 10, 30,
-                            1e-3, 0, 0, 12.0, 0, 1, 0, None)
+                            1e-3, 0, 0, 12.0, 0, 1, 0, None, None, None, None, None, None)
     assert rc == -3 and b"ghost" in lib.tmb_last_error()
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_explicit_ghost_pointers(half):
+    """The ghost planes may live anywhere (on the multi-GPU path they are the neighbour GPU's own
+    buffers, read over NVLink): two shards of one volume, each reading the other's boundary planes
+    in place through u_lo / p*_lo / u_hi -- no copies at all -- give the whole-volume result."""
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr, stream_ptr
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy, ROF_TV_cupy
+
+    v = _vol((40, 20, 64), 21)
+    nz, ny, nx = v.shape
+    cut, iters = 24, 6
+    pdt = torch.float16 if half else torch.float32
+    bounds = [(0, cut), (cut, nz)]
+    # own planes only: no ghost slots
+    U = [[torch.zeros((b - a, ny, nx), device="cuda") for (a, b) in bounds] for _ in range(2)]
+    P = [[[torch.zeros((b - a, ny, nx), dtype=pdt, device="cuda") for _ in range(3)] for (a, b) in bounds]
+         for _ in range(2)]
+    D = [v[a:b].contiguous() for (a, b) in bounds]
+    for i in range(2):
+        U[0][i].copy_(D[i])
+    for it in range(iters):
+        a, b = it % 2, 1 - it % 2
+        n0 = cut
+        # shard 0: ghost above = first plane of shard 1; shard 1: ghosts below = last plane of shard 0
+        check(lib.tmb_pd_tv_iter(ptr(D[0]), ptr(U[a][0]), ptr(U[b][0]), *[ptr(P[a][0][c]) for c in range(3)],
+                                 *[ptr(P[b][0][c]) for c in range(3)], n0, ny, nx, 4e-4, 0, 1, 12.0, int(half), 0, 1,
+                                 None, None, None, None, ptr(U[a][1][0]), stream_ptr(v)), "tmb_pd_tv_iter")
+        check(lib.tmb_pd_tv_iter(ptr(D[1]), ptr(U[a][1]), ptr(U[b][1]), *[ptr(P[a][1][c]) for c in range(3)],
+                                 *[ptr(P[b][1][c]) for c in range(3)], nz - cut, ny, nx, 4e-4, 0, 1, 12.0, int(half),
+                                 1, 0, ptr(U[a][0][n0 - 1]), *[ptr(P[a][0][c][n0 - 1]) for c in range(3)], None,
+                                 stream_ptr(v)), "tmb_pd_tv_iter")
+    got = torch.cat([U[iters % 2][0], U[iters % 2][1]], dim=0)
+    assert torch.equal(got, PD_TV_cupy(v, 4e-4, iters, 0, 1, 12.0, 0, half))
+
+    R = [[torch.zeros((b - a, ny, nx), device="cuda") for (a, b) in bounds] for _ in range(2)]
+    for i in range(2):
+        R[0][i].copy_(D[i])
+    for it in range(iters):
+        a, b = it % 2, 1 - it % 2
+        check(lib.tmb_rof_tv_iter(ptr(D[0]), ptr(R[a][0]), ptr(R[b][0]), cut, ny, nx, 4e-4, 1e-3, int(half), 0, 1,
+                                  None, ptr(R[a][1][0]), stream_ptr(v)), "tmb_rof_tv_iter")
+        check(lib.tmb_rof_tv_iter(ptr(D[1]), ptr(R[a][1]), ptr(R[b][1]), nz - cut, ny, nx, 4e-4, 1e-3, int(half), 1, 0,
+                                  ptr(R[a][0][cut - 2]), None, stream_ptr(v)), "tmb_rof_tv_iter")
+    got = torch.cat([R[iters % 2][0], R[iters % 2][1]], dim=0)
+    assert torch.equal(got, ROF_TV_cupy(v, 4e-4, iters, 1e-3, 0, half))

@@ -85,6 +85,7 @@ class RecToolsIRCuPy:
         self.nonneg_regul = 0
         self.power_seed = 0  # the reference draws an unseeded cp.random.randn (:326)
         self.zshard = None   # set_zshard(): this object reconstructs one z-block of a larger volume
+        self.tv_peer_memory = None  # sharded TV halos: None = NVLink peer loads on NCCL, False = messages
         self._sharded_tv = {}
 
     def set_zshard(self, shard) -> None:
@@ -275,7 +276,7 @@ class RecToolsIRCuPy:
 
                 key = ("rof", tuple(X.shape), bool(reg.get("half_precision", False)))
                 if key not in self._sharded_tv:
-                    self._sharded_tv = {key: ShardedROFTV(sh, key[1], X.device, key[2])}
+                    self._sharded_tv = {key: ShardedROFTV(sh, key[1], X.device, key[2], self.tv_peer_memory)}
                 return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["time_marching_step"],
                                              out=out)
             return ROF_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["time_marching_step"], dev,
@@ -287,7 +288,7 @@ class RecToolsIRCuPy:
 
                 key = ("pd", tuple(X.shape), bool(reg.get("half_precision", False)))
                 if key not in self._sharded_tv:
-                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2])}
+                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2], self.tv_peer_memory)}
                 return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["methodTV"],
                                              self.nonneg_regul, reg["PD_LipschitzConstant"], out=out)
             return PD_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["methodTV"], self.nonneg_regul,

@@ -9,12 +9,14 @@ the shards:
 * scalars: the power method's norm (methodsIR_CuPy.py:333-351), the PWLS weight normalisation
   ``w.max()`` (:394-395), CGLS inner products (:270-289)  ->  one scalar all-reduce each;
 * 3-D total variation: the forward z difference and the backward z divergence reach one plane into
-  the neighbouring shards (primal_dual_for_total_variation.cu:188-194, 244-252).  ``ShardedPDTV``
-  keeps one ghost plane below / above the shard and refreshes it with point-to-point messages
-  between the inner iterations; the result is bit-identical to the whole-volume prox;
+  the neighbouring shards (primal_dual_for_total_variation.cu:188-194, 244-252).  ``ShardedPDTV`` /
+  ``ShardedROFTV`` let the TV kernel read the neighbours' boundary planes directly over NVLink
+  (buffers in symmetric memory, peer pointers, one cross-GPU barrier per inner iteration) or, as a
+  fallback, refresh ghost planes with point-to-point messages; either way the result is
+  bit-identical to the whole-volume prox;
 * the final volume: one all-gather (``ZShard.all_gather_volume``).
 
-Nothing here touches the CUDA library except ``ShardedPDTV``; the rest runs on any backend
+Nothing here touches the CUDA library except the two ``Sharded*TV`` classes; the rest runs on any backend
 (``gloo`` on CPU tensors in the unit tests, ``nccl`` on the GPUs).
 """
 
@@ -123,22 +125,85 @@ class ZShard:
         return out[: self.nz_total]
 
 
+class _PeerSlab:
+    """One buffer per rank, allocated from torch's symmetric memory and mapped into every peer's
+    address space over NVLink / NVSwitch (``torch.distributed._symmetric_memory``).  The layout is
+    the same on all ranks, so a neighbour's array lives at ``buffer_ptrs[neighbour] + offset``."""
+
+    def __init__(self, nbytes: int, device: torch.device, group: Optional[dist.ProcessGroup]):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = list(self.hdl.buffer_ptrs)
+
+    def view(self, offset: int, shape, dtype) -> torch.Tensor:
+        n = int(torch.empty((), dtype=dtype).element_size())
+        for d in shape:
+            n *= int(d)
+        return self.buf[offset:offset + n].view(dtype).view(*shape)
+
+    def barrier(self) -> None:
+        """Cross-GPU barrier on the current stream (signal pads in peer memory)."""
+        self.hdl.barrier(0)
+
+
+def _peer_memory_default(shard: "ZShard", device: torch.device) -> bool:
+    return shard.world > 1 and device.type == "cuda" and dist.get_backend(shard.group) == "nccl"
+
+
 class ShardedPDTV:
     """PD_TV prox of a z-sharded 3-D volume, bit-identical to ``PD_TV_cupy`` on the whole volume.
 
-    Per inner iteration each rank sends its top plane of U and of P1..P3 to the next rank and its
-    bottom plane of U to the previous one (5 planes), then launches ``tmb_pd_tv_iter`` with the
-    ghost flags of its position.  Buffers are allocated once and reused across calls."""
+    Two ways of getting the one-plane halos (top plane of U and P1..P3 of the previous shard, bottom
+    plane of U of the next one):
 
-    def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False):
+    * ``peer_memory=True`` (default on NCCL): the ping-pong buffers live in symmetric memory and the
+      kernel reads the neighbours' planes **directly over NVLink** through peer pointers
+      (``tmb_pd_tv_iter(..., u_lo, p*_lo, u_hi)``): compute and halo transfer are one kernel, the
+      host only places a cross-GPU barrier between iterations;
+    * ``peer_memory=False``: ghost planes next to the shard, refreshed with point-to-point messages
+      (5 planes per rank per iteration) before each launch.
+
+    Buffers are allocated once and reused across calls."""
+
+    def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False,
+                 peer_memory: Optional[bool] = None):
         nzl, ny, nx = shape
         if nzl != shard.nz_local:
             raise ValueError("ShardedPDTV: the volume shard does not match the z-partition")
         self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
+        self.peer = _peer_memory_default(shard, device) if peer_memory is None else bool(peer_memory)
         pdt = torch.float16 if self.half else torch.float32
         # U: ghost plane below (index 0) and above (index nzl + 1); P: ghost plane below only
-        self.U = [torch.zeros((nzl + 2, ny, nx), dtype=torch.float32, device=device) for _ in range(2)]
-        self.P = [[torch.zeros((nzl + 1, ny, nx), dtype=pdt, device=device) for _ in range(3)] for _ in range(2)]
+        if not self.peer:
+            self.U = [torch.zeros((nzl + 2, ny, nx), dtype=torch.float32, device=device) for _ in range(2)]
+            self.P = [[torch.zeros((nzl + 1, ny, nx), dtype=pdt, device=device) for _ in range(3)] for _ in range(2)]
+            return
+        per = shard_bounds(shard.nz_total, shard.world, 0, shard.multiple)[1]  # largest shard: common layout
+        plane = ny * nx
+        esz = 2 if self.half else 4
+        self._ub, self._pb = (per + 2) * plane * 4, (per + 1) * plane * esz
+        self._plane, self._esz = plane, esz
+        self.slab = _PeerSlab(2 * self._ub + 6 * self._pb, device, shard.group)
+        self.slab.buf.zero_()
+        self.U = [self.slab.view(a * self._ub, (nzl + 2, ny, nx), torch.float32) for a in range(2)]
+        self.P = [[self.slab.view(2 * self._ub + (a * 3 + c) * self._pb, (nzl + 1, ny, nx), pdt) for c in range(3)]
+                  for a in range(2)]
+
+    def _ghost_ptrs(self, a: int):
+        """Peer addresses of the halo planes of ping-pong set ``a``."""
+        sh, plane, esz = self.shard, self._plane, self._esz
+        u_lo = p_lo = u_hi = None
+        if sh.prev is not None:
+            base = self.slab.ptrs[sh._global(sh.prev)]
+            z0p, z1p = shard_bounds(sh.nz_total, sh.world, sh.prev, sh.multiple)
+            top = z1p - z0p  # index of the previous shard's last own plane (its plane 0 is a ghost)
+            u_lo = base + a * self._ub + top * plane * 4
+            p_lo = [base + 2 * self._ub + (a * 3 + c) * self._pb + top * plane * esz for c in range(3)]
+        if sh.next is not None:
+            u_hi = self.slab.ptrs[sh._global(sh.next)] + a * self._ub + plane * 4  # its first own plane
+        return u_lo, p_lo, u_hi
 
     def __call__(self, data: torch.Tensor, regularisation_parameter: float, iterations: int, methodTV: int = 0,
                  nonneg: int = 0, lipschitz_const: float = 8.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -150,6 +215,8 @@ class ShardedPDTV:
         if tuple(data.shape) != self.shape or data.dtype != torch.float32 or not data.is_contiguous():
             raise ValueError(f"ShardedPDTV: expected a contiguous float32 volume shard of shape {self.shape}")
         U, P = self.U, self.P
+        if self.peer:
+            self.slab.barrier()  # nobody still reads the buffers of the previous call
         U[0][1:nzl + 1].copy_(data)
         for c in range(3):
             P[0][c].zero_()
@@ -157,15 +224,23 @@ class ShardedPDTV:
         with torch.cuda.device(self.device):
             for it in range(int(iterations)):
                 a, b = it % 2, 1 - it % 2
-                up = [(U[a][nzl], U[a][0])]
-                if it > 0:  # the dual variable starts at zero everywhere
-                    up += [(P[a][c][nzl], P[a][c][0]) for c in range(3)]
-                sh.exchange_halos(up, [(U[a][1], U[a][nzl + 1])])
+                u_lo = p_lo = u_hi = None
+                if self.peer:
+                    # every rank has finished writing set `a` (and reading set `b`): one barrier per
+                    # iteration replaces the halo messages, the kernel loads the planes over NVLink
+                    self.slab.barrier()
+                    u_lo, p_lo, u_hi = self._ghost_ptrs(a)
+                else:
+                    up = [(U[a][nzl], U[a][0])]
+                    if it > 0:  # the dual variable starts at zero everywhere
+                        up += [(P[a][c][nzl], P[a][c][0]) for c in range(3)]
+                    sh.exchange_halos(up, [(U[a][1], U[a][nzl + 1])])
+                p_lo = p_lo or [None, None, None]
                 check(lib.tmb_pd_tv_iter(ptr(data), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
                                          ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
                                          nzl, ny, nx, float(regularisation_parameter), int(methodTV), int(nonneg),
                                          float(lipschitz_const), int(self.half), ghost_lo, ghost_hi,
-                                         stream_ptr(data)), "tmb_pd_tv_iter")
+                                         u_lo, p_lo[0], p_lo[1], p_lo[2], u_hi, stream_ptr(data)), "tmb_pd_tv_iter")
         res = U[int(iterations) % 2][1:nzl + 1]
         if out is None:
             return res.clone()
@@ -178,17 +253,39 @@ class ShardedROFTV:
 
     The normalised z difference of the plane below a shard enters the divergence at its first
     plane (rudin_osher_fatemi_total_variation.cu:170-181, 235), and that difference itself needs
-    the plane below it: two ghost planes below, one above.  Per inner iteration each rank sends its
-    top two planes to the next rank and its bottom plane to the previous one."""
+    the plane below it: two ghost planes below, one above -- read over NVLink from the neighbours'
+    buffers (``peer_memory=True``, one cross-GPU barrier per iteration) or refreshed with messages
+    (top two planes to the next rank, bottom plane to the previous one)."""
 
-    def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False):
+    def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False,
+                 peer_memory: Optional[bool] = None):
         nzl, ny, nx = shape
         if nzl != shard.nz_local:
             raise ValueError("ShardedROFTV: the volume shard does not match the z-partition")
         if shard.world > 1 and nzl < 2:
             raise ValueError("ShardedROFTV: every shard needs at least two slices")
         self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
-        self.U = [torch.zeros((nzl + 3, ny, nx), dtype=torch.float32, device=device) for _ in range(2)]
+        self.peer = _peer_memory_default(shard, device) if peer_memory is None else bool(peer_memory)
+        if not self.peer:
+            self.U = [torch.zeros((nzl + 3, ny, nx), dtype=torch.float32, device=device) for _ in range(2)]
+            return
+        per = shard_bounds(shard.nz_total, shard.world, 0, shard.multiple)[1]
+        self._plane = ny * nx
+        self._ub = (per + 3) * self._plane * 4
+        self.slab = _PeerSlab(2 * self._ub, device, shard.group)
+        self.slab.buf.zero_()
+        self.U = [self.slab.view(a * self._ub, (nzl + 3, ny, nx), torch.float32) for a in range(2)]
+
+    def _ghost_ptrs(self, a: int):
+        sh, plane = self.shard, self._plane
+        u_lo = u_hi = None
+        if sh.prev is not None:
+            z0p, z1p = shard_bounds(sh.nz_total, sh.world, sh.prev, sh.multiple)
+            # the previous shard's last two own planes (its planes 0 and 1 are ghosts)
+            u_lo = self.slab.ptrs[sh._global(sh.prev)] + a * self._ub + (z1p - z0p) * plane * 4
+        if sh.next is not None:
+            u_hi = self.slab.ptrs[sh._global(sh.next)] + a * self._ub + 2 * plane * 4
+        return u_lo, u_hi
 
     def __call__(self, data: torch.Tensor, regularisation_parameter: float, iterations: int,
                  time_marching_parameter: float = 0.001, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -200,15 +297,23 @@ class ShardedROFTV:
         if tuple(data.shape) != self.shape or data.dtype != torch.float32 or not data.is_contiguous():
             raise ValueError(f"ShardedROFTV: expected a contiguous float32 volume shard of shape {self.shape}")
         U = self.U
+        if self.peer:
+            self.slab.barrier()
         U[0][2:nzl + 2].copy_(data)
         ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
         with torch.cuda.device(self.device):
             for it in range(int(iterations)):
                 a, b = it % 2, 1 - it % 2
-                sh.exchange_halos([(U[a][nzl:nzl + 2], U[a][0:2])], [(U[a][2], U[a][nzl + 2])])
+                u_lo = u_hi = None
+                if self.peer:
+                    self.slab.barrier()
+                    u_lo, u_hi = self._ghost_ptrs(a)
+                else:
+                    sh.exchange_halos([(U[a][nzl:nzl + 2], U[a][0:2])], [(U[a][2], U[a][nzl + 2])])
                 check(lib.tmb_rof_tv_iter(ptr(data), ptr(U[a][2:]), ptr(U[b][2:]), nzl, ny, nx,
                                           float(regularisation_parameter), float(time_marching_parameter),
-                                          int(self.half), ghost_lo, ghost_hi, stream_ptr(data)), "tmb_rof_tv_iter")
+                                          int(self.half), ghost_lo, ghost_hi, u_lo, u_hi, stream_ptr(data)),
+                          "tmb_rof_tv_iter")
         res = U[int(iterations) % 2][2:nzl + 2]
         if out is None:
             return res.clone()
