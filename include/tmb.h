@@ -61,8 +61,8 @@ int tmb_geom_table(const tmb_geom *g, float *out);
 size_t tmb_geom_workspace_bytes(const tmb_geom *g);
 
 /* Debug/test switch read by tmb_geom_create: 0 = choose the forward-projector kernel by stack height
- * (k_fpq with the 32-slice-blocked layouts from 17 slices up, else k_fp), 1 = k_fp, 2 = k_fpq.
- * Returns the old value. */
+ * (k_fpq with the 32-slice-blocked layouts from 17 slices up, else k_fp), 1 = k_fp, 2 = k_fpq,
+ * 3 = k_fpq with one 32-slice group per CTA only.  Returns the old value. */
 int tmb_fp_set_kernel(int mode);
 
 /* ---- projector pair --------------------------------------------------------------------

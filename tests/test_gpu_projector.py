@@ -156,10 +156,12 @@ def test_linearity_and_zero_at_scale():
     assert abs(lhs - rhs) / max(abs(lhs), abs(rhs)) < 5e-2
 
 
-@pytest.mark.parametrize("nz,n,nu,na,os_n", [(5, 64, 80, 36, 3), (20, 130, 130, 50, None), (70, 48, 40, 21, 2)])
+@pytest.mark.parametrize("nz,n,nu,na,os_n", [(5, 64, 80, 36, 3), (20, 130, 130, 50, None), (70, 48, 40, 21, 2),
+                                             (64, 40, 64, 12, None)])
 def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
-    """k_fp (8 slices per thread) and k_fpq (bank-conflict-free 32-slice blocks) share their
-    arithmetic: plain projection and the fused gradient are bit-identical."""
+    """k_fp (8 slices per thread), k_fpq (bank-conflict-free 32-slice blocks; two blocks per CTA =
+    mode 2, one = mode 3) share their arithmetic: plain projection and the fused gradient are
+    bit-identical."""
     from tomobar_b200._lib import lib
     from tomobar_b200.projector import ProjTools3D
 
@@ -168,14 +170,15 @@ def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
     b = torch.randn((nz, na, nu), device="cuda", generator=g)
     w = torch.rand((nz, na, nu), device="cuda", generator=g)
     res = {}
-    for mode in (1, 2):
-        old = lib.tmb_fp_set_kernel(mode)
+    for mode in (1, 2, 3):
+        lib.tmb_fp_set_kernel(mode)
         try:
             P = ProjTools3D(nu, 0, nz, _angles(na), 0.5, n, "gpu", 0, os_n)
+            sub = None if os_n is None else os_n - 1
+            fp = P._forwprojCuPy(vol) if os_n is None else P._forwprojOSCuPy(vol, sub)
+            res[mode] = (fp, P.grad_data_term(vol, b, sub, "PWLS", w), P.grad_data_term(vol, b.abs(), sub, "KL"))
         finally:
-            lib.tmb_fp_set_kernel(old)
-        sub = None if os_n is None else os_n - 1
-        fp = P._forwprojCuPy(vol) if os_n is None else P._forwprojOSCuPy(vol, sub)
-        res[mode] = (fp, P.grad_data_term(vol, b, sub, "PWLS", w), P.grad_data_term(vol, b.abs(), sub, "KL"))
-    for a, c in zip(res[1], res[2]):
-        assert torch.equal(a, c)
+            lib.tmb_fp_set_kernel(0)
+    for mode in (2, 3):
+        for a, c in zip(res[1], res[mode]):
+            assert torch.equal(a, c)

@@ -10,6 +10,7 @@ namespace tmb {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int subset_size(const tmb_geom *g, int subset);
+extern int g_fpq_single;
 static std::atomic<uint64_t> g_next_id{1};
 // test hook: which forward-projector kernel geometries created from now on use
 // (0 = by stack height, 1 = k_fp, 2 = k_fpq)
@@ -20,8 +21,9 @@ using namespace tmb;
 
 extern "C" int tmb_version(void) { return 100; }
 extern "C" int tmb_fp_set_kernel(int mode) {
-  const int old = g_fp_kernel;
-  g_fp_kernel = (mode == 1 || mode == 2) ? mode : 0;
+  const int old = g_fp_kernel + (g_fpq_single ? 1 : 0);
+  g_fp_kernel = (mode == 1) ? 1 : ((mode == 2 || mode == 3) ? 2 : 0);
+  g_fpq_single = mode == 3;
   return old;
 }
 extern "C" const char *tmb_last_error(void) { return g_err.c_str(); }

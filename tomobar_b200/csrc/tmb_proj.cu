@@ -270,6 +270,7 @@ struct FpArgs {
   const float *w;    // mode 1: PWLS weights (same layout) or nullptr
   int n, nu, up, qp, nz, na_loc, na_tot;
   int nzc_alloc;          // z-chunks S_int holds (k_fpq's 32-slice groups may reach past it)
+  int zg_first;           // k_fpq: z-group of blockIdx.z == 0
   int a_first, a_stride;  // constant-table slot of local angle j
   int g_first, g_stride;  // global angle index (row of b / w) of local angle j
   int j_begin;            // local angle of blockIdx.y == 0
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
 // its wavefronts are bank conflicts.)  CTA = FQ_K bins x 32 slices = 512 consumer threads + one
 // producer warp that streams FQ_G lines per stage with one bulk copy (TMA) per line.
 // ==========================================================================================
-constexpr int FQ_G = 3;       // volume lines per pipeline stage
+constexpr int FQ_G = 3;       // volume lines per pipeline stage (one z-group per CTA)
+constexpr int FQ_G2 = 2;      // ... with two z-groups per CTA (twice the bytes per line)
 constexpr int FQ_STAGES = 3;
 constexpr int FQ_THREADS = FQ_K * FQ_CG;
 
@@ -460,17 +462,22 @@ __global__ void k_vol_to_intq(const float *__restrict__ vol, float4 *__restrict_
   }
 }
 
-__global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
+// NG = z-groups (of 32 slices) per CTA.  With NG = 2 a thread carries two accumulators (8 slices)
+// and its index / weight arithmetic is amortised over twice the updates (the kernel is otherwise
+// issue-bound: ncu, profiles/); NG = 1 serves stacks of at most 32 slices and an odd last group.
+template <int NG>
+__global__ void __launch_bounds__(FQ_THREADS + 32, NG == 1 ? 2 : 1) k_fpq(const FpArgs p) {
+  constexpr int G = NG == 1 ? FQ_G : FQ_G2;  // volume lines per stage
   extern __shared__ __align__(128) unsigned char fp_smem[];
-  // buf[stage][line][position][chunk]
-  float4(*buf)[FQ_G][FQ_W][FQ_CG] = reinterpret_cast<float4(*)[FQ_G][FQ_W][FQ_CG]>(fp_smem);
-  __shared__ int wst[FQ_STAGES][FQ_G];
+  // buf[stage][line][group][position][chunk]
+  float4(*buf)[G][NG][FQ_W][FQ_CG] = reinterpret_cast<float4(*)[G][NG][FQ_W][FQ_CG]>(fp_smem);
+  __shared__ int wst[FQ_STAGES][G];
   __shared__ __align__(8) uint64_t full_bar[FQ_STAGES], empty_bar[FQ_STAGES];
 
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * FQ_K;
   const int j = p.j_begin + blockIdx.y;  // local angle
-  const int zg = blockIdx.z;
+  const int zg0 = p.zg_first + blockIdx.z * NG;
   const float4 t = c_fp[p.a_first + j * p.a_stride];
   const float alpha = t.x, b0 = t.y, bstep = t.z;
   const float scale = fabsf(t.w);
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
   }
   __syncthreads();
 
-  const int n_iter = (p.n + FQ_G - 1) / FQ_G;
+  const int n_iter = (p.n + G - 1) / G;
   const int win = min(FQ_W, (int)ceilf((float)(FQ_K - 1) * fabsf(bstep)) + 4);
 
   if (tid >= FQ_THREADS) {
@@ -494,12 +501,13 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
       const float beta_a = fmaf((float)k0, bstep, b0);
       const float beta_b = fmaf((float)(k0 + FQ_K - 1), bstep, b0);
       const float beta_min = fminf(beta_a, beta_b);
+      const uint32_t line_bytes = (uint32_t)(win * FQ_CG * sizeof(float4));
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % FQ_STAGES;
         const uint32_t ph = (it / FQ_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const int m0 = it * FQ_G;
-        const int ng = min(FQ_G, p.n - m0);
+        const int m0 = it * G;
+        const int ng = min(G, p.n - m0);
         for (int gm = 0; gm < ng; ++gm) {
           const float xm = (float)(m0 + gm) - half + 0.5f;
           int ws = (int)floorf(fmaf(alpha, xm, beta_min)) - 1;
@@ -507,10 +515,14 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
           wst[s][gm] = ws;
         }
         // the arrive releases the window starts to the consumers that acquire the completed phase
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * win * FQ_CG * sizeof(float4)));
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(ng * NG) * line_bytes);
         for (int gm = 0; gm < ng; ++gm) {
-          const float4 *src = vsrc + (((size_t)zg * p.n + (m0 + gm)) * p.qp + (QPAD + wst[s][gm])) * FQ_CG;
-          bulk_g2s(&buf[s][gm][0][0], src, (uint32_t)(win * FQ_CG * sizeof(float4)), &full_bar[s]);
+#pragma unroll
+          for (int q = 0; q < NG; ++q) {
+            const float4 *src =
+                vsrc + (((size_t)(zg0 + q) * p.n + (m0 + gm)) * p.qp + (QPAD + wst[s][gm])) * FQ_CG;
+            bulk_g2s(&buf[s][gm][q][0][0], src, line_bytes, &full_bar[s]);
+          }
         }
       }
     }
@@ -521,20 +533,22 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
   const int cc = tid & (FQ_CG - 1);  // z-chunk inside the group
   const int k = k0 + (tid >> 3);     // detector bin
   const float beta = fmaf((float)k, bstep, b0);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[NG];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const bool quant = p.quant != 0;
   for (int it = 0; it < n_iter; ++it) {
     const int s = it % FQ_STAGES;
     const uint32_t ph = (it / FQ_STAGES) & 1;
     mbar_wait(&full_bar[s], ph);
-    const int m0 = it * FQ_G;
-    const int ng = min(FQ_G, p.n - m0);
+    const int m0 = it * G;
+    const int ng = min(G, p.n - m0);
     // (float)(m0 + gm) - half + 0.5f: integers and halves below 2^24 are exact, so base + gm is identical
     const float xbase = (float)m0 - half + 0.5f;
-    const float4 *sbuf = &buf[s][0][0][cc];
+    const float4 *sbuf = &buf[s][0][0][0][cc];
 #pragma unroll
-    for (int gm = 0; gm < FQ_G; ++gm) {
+    for (int gm = 0; gm < G; ++gm) {
       if (gm < ng) {
         const float rho = fmaf(alpha, xbase + (float)gm, beta);
         // floor and round-to-nearest-even without the quarter-rate conversion pipe: one F2I, the
@@ -544,8 +558,11 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
         if (quant) f = ((f * 256.0f + 12582912.0f) - 12582912.0f) * (1.0f / 256.0f);
         const float g = 1.0f - f;
         const int i = max(0, min(ifl - wst[s][gm], win - 2));
-        const float4 *q = sbuf + (gm * FQ_W + i) * FQ_CG;
-        lerp_acc(acc, g, f, q[0], q[FQ_CG]);
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+          const float4 *e = sbuf + ((gm * NG + q) * FQ_W + i) * FQ_CG;
+          lerp_acc(acc[q], g, f, e[0], e[FQ_CG]);
+        }
       }
     }
     __syncwarp();
@@ -553,36 +570,38 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpq(const FpArgs p) {
   }
 
   if (k >= p.nu) return;
-  const int zc = zg * FQ_CG + cc;
-  float *a4 = reinterpret_cast<float *>(&acc);
-  if (p.mode == 0) {
 #pragma unroll
-    for (int q = 0; q < ZC; ++q) {
-      const int z = zc * ZC + q;
-      if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[q], scale);
-    }
-  } else {
-    // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
-    if (zc * ZC >= p.nzc_alloc * ZC) return;
-    const int ga = p.g_first + j * p.g_stride;
-    float r[ZC];
+  for (int q = 0; q < NG; ++q) {
+    const int zc = (zg0 + q) * FQ_CG + cc;
+    float *a4 = reinterpret_cast<float *>(&acc[q]);
+    if (p.mode == 0) {
 #pragma unroll
-    for (int q = 0; q < ZC; ++q) {
-      const int z = zc * ZC + q;
-      float v = 0.f;
-      if (z < p.nz) {
-        const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
-        const float ax = __fmul_rn(a4[q], scale);
-        if (p.fidelity == TMB_FID_KL) {
-          v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
-        } else {
-          v = __fsub_rn(ax, p.b[idx]);
-          if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
-        }
+      for (int e = 0; e < ZC; ++e) {
+        const int z = zc * ZC + e;
+        if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[e], scale);
       }
-      r[q] = v;
+    } else if (zc < p.nzc_alloc) {
+      // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
+      const int ga = p.g_first + j * p.g_stride;
+      float r[ZC];
+#pragma unroll
+      for (int e = 0; e < ZC; ++e) {
+        const int z = zc * ZC + e;
+        float v = 0.f;
+        if (z < p.nz) {
+          const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
+          const float ax = __fmul_rn(a4[e], scale);
+          if (p.fidelity == TMB_FID_KL) {
+            v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
+          } else {
+            v = __fsub_rn(ax, p.b[idx]);
+            if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
+          }
+        }
+        r[e] = v;
+      }
+      p.sint[((size_t)zc * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
     }
-    p.sint[((size_t)zc * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -673,6 +692,8 @@ __global__ void k_resid_post(const PostArgs p) {
 // ==========================================================================================
 // host-side launchers
 // ==========================================================================================
+// test hook (tmb_fp_set_kernel(3)): run the Q path with one z-group per CTA only
+int g_fpq_single = 0;
 static int subset_first(const tmb_geom *g, int subset) { return subset < 0 ? 0 : subset; }
 static int subset_stride(const tmb_geom *g, int subset) { return subset < 0 ? 1 : g->os_number; }
 int subset_size(const tmb_geom *g, int subset) {
@@ -737,14 +758,14 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
   a.na_loc = na_loc; a.na_tot = g->d.na; a.nzc_alloc = g->d.nzc;
   a.g_first = first; a.g_stride = stride;
   a.mode = mode; a.fidelity = fidelity; a.quant = g->quant8;
-  const size_t smem = g->fp_q ? sizeof(float4) * FQ_STAGES * FQ_G * FQ_W * FQ_CG
-                              : sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W;
+  const size_t smem = sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W;
+  const size_t smem_q1 = sizeof(float4) * FQ_STAGES * FQ_G * FQ_W * FQ_CG;
+  const size_t smem_q2 = sizeof(float4) * FQ_STAGES * FQ_G2 * 2 * FQ_W * FQ_CG;
   static bool attr_set = false;
   if (!attr_set) {
-    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W)));
-    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fpq, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(float4) * FQ_STAGES * FQ_G * FQ_W * FQ_CG)));
+    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fpq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q1));
+    TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fpq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q2));
     attr_set = true;
   }
   int j = 0;
@@ -759,8 +780,18 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
     a.j_begin = j;
     // grid.y is limited to 65535: far above any angle count
     if (g->fp_q) {
-      dim3 gridq((g->d.nu + FQ_K - 1) / FQ_K, cnt, g->d.nzg);
-      k_fpq<<<gridq, FQ_THREADS + 32, smem, st>>>(a);
+      // pairs of z-groups per CTA, a last odd group on its own
+      const int pairs = g_fpq_single ? 0 : g->d.nzg / 2;
+      if (pairs > 0) {
+        a.zg_first = 0;
+        dim3 gridq((g->d.nu + FQ_K - 1) / FQ_K, cnt, pairs);
+        k_fpq<2><<<gridq, FQ_THREADS + 32, smem_q2, st>>>(a);
+      }
+      if (g->d.nzg - 2 * pairs > 0) {
+        a.zg_first = 2 * pairs;
+        dim3 gridq((g->d.nu + FQ_K - 1) / FQ_K, cnt, g->d.nzg - 2 * pairs);
+        k_fpq<1><<<gridq, FQ_THREADS + 32, smem_q1, st>>>(a);
+      }
     } else {
       dim3 grid((g->d.nu + FP_K - 1) / FP_K, cnt, g->d.nzc / NZC);
       k_fp<<<grid, FP_K + 32, smem, st>>>(a);

@@ -39,9 +39,19 @@ def main():
     print(f"BACKPROJ    {n}x{n}x{nz}, {na} angles: {ms:9.2f} ms  ({upd / ms / 1e6:8.1f} GUPS, "
           f"{float(nz) * na * n / ms / 1e6:6.2f} GProj/s)", flush=True)
     vol = torch.rand((nz, n, n), device="cuda", generator=g)
-    ms = timed(lambda: R.FORWPROJ(vol))
-    print(f"FORWPROJ    {n}x{n}x{nz}, {na} angles: {ms:9.2f} ms  ({upd / ms / 1e6:8.1f} GUPS, "
-          f"{float(nz) * na * n / ms / 1e6:6.2f} GProj/s)", flush=True)
+    from tomobar_b200._lib import lib
+
+    for mode, name in ((0, "default"), (1, "k_fp"), (3, "k_fpq<1>"), (2, "k_fpq<2>")):
+        lib.tmb_fp_set_kernel(mode)
+        try:
+            Rm = RecToolsDIRCuPy(n, 0, nz, 0.0, angles, n, device_projector=0)
+            ms = timed(lambda: Rm.FORWPROJ(vol))
+        finally:
+            lib.tmb_fp_set_kernel(0)
+        print(f"FORWPROJ {name:9s} {n}x{n}x{nz}, {na} angles: {ms:9.2f} ms  ({upd / ms / 1e6:8.1f} GUPS, "
+              f"{float(nz) * na * n / ms / 1e6:6.2f} GProj/s)", flush=True)
+        del Rm
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
