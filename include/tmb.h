@@ -61,9 +61,13 @@ int tmb_geom_table(const tmb_geom *g, float *out);
 size_t tmb_geom_workspace_bytes(const tmb_geom *g);
 
 /* Debug/test switch read by tmb_geom_create: 0 = choose the forward-projector kernel by stack height
- * (k_fpq with the 32-slice-blocked layouts from 17 slices up, else k_fp), 1 = k_fp, 2 = k_fpq,
- * 3 = k_fpq with one 32-slice group per CTA only.  Returns the old value. */
+ * (k_fpq with the 32-slice-blocked layouts from 17 slices up, else k_fp), 1 = k_fp, 2 = k_fpq
+ * (line-segmented for L2 reuse), 3 = k_fpq with two 32-slice groups per CTA and no segments,
+ * 4 = k_fpq without segments.  Returns the old value. */
 int tmb_fp_set_kernel(int mode);
+/* Debug/test switch read by tmb_geom_create: forced k_fpq line-segment length (0 = sized so that a
+ * segment of both marching directions fits the L2).  Returns the old value. */
+int tmb_fp_set_segment(int lines);
 
 /* ---- projector pair --------------------------------------------------------------------
  * tmb_fp3d replaces AstraBase.runAstraProj3DCuPy -> astra direct_FP3D (astra_base.py:560-606)

@@ -140,9 +140,13 @@ def test_linearity_and_zero_at_scale():
         assert torch.count_nonzero(P._forwprojOSCuPy(torch.zeros_like(x), s)) == 0
         bx = P._backprojOSCuPy(fx, s)
         assert torch.isfinite(bx).all()
-    # slices are independent: projecting a sub-stack equals slicing the projection
+    # slices are independent: permuting the stack permutes the projection (bit for bit), and projecting
+    # a sub-stack equals slicing the projection (an 8-slice stack runs k_fp, the 24-slice one the
+    # line-segmented k_fpq, which adds its partial sums in a different order: fp32 rounding)
+    assert torch.equal(P._forwprojOSCuPy(x.flip(0).contiguous(), 3), P._forwprojOSCuPy(x, 3).flip(0))
     P2 = ProjTools3D(n, 0, 8, angles, 0.0, n, "gpu", 0, 6)
-    assert torch.equal(P2._forwprojOSCuPy(x[8:16].contiguous(), 3), P._forwprojOSCuPy(x, 3)[8:16])
+    assert rel_max(P2._forwprojOSCuPy(x[8:16].contiguous(), 3).cpu().numpy(),
+                   P._forwprojOSCuPy(x, 3)[8:16].cpu().numpy()) < 2e-6
     # unmatched pair is still close to adjoint: <Ax, y> ~ <x, A^T y>
     full = ProjTools3D(n, 0, nz, angles, 0.0, n)
     # (smooth inputs: on white noise the Joseph / voxel-driven pair differs by >10 %)
@@ -159,9 +163,9 @@ def test_linearity_and_zero_at_scale():
 @pytest.mark.parametrize("nz,n,nu,na,os_n", [(5, 64, 80, 36, 3), (20, 130, 130, 50, None), (70, 48, 40, 21, 2),
                                              (64, 40, 64, 12, None)])
 def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
-    """k_fp (8 slices per thread), k_fpq (bank-conflict-free 32-slice blocks; two blocks per CTA =
-    mode 2, one = mode 3) share their arithmetic: plain projection and the fused gradient are
-    bit-identical."""
+    """k_fp (8 slices per thread) and k_fpq (bank-conflict-free 32-slice blocks): one block per CTA
+    (mode 4), two (mode 3) are bit-identical to k_fp; the line-segmented default (mode 2, segments
+    forced short here) adds its partial sums in a different order and agrees to fp32 rounding."""
     from tomobar_b200._lib import lib
     from tomobar_b200.projector import ProjTools3D
 
@@ -170,8 +174,9 @@ def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
     b = torch.randn((nz, na, nu), device="cuda", generator=g)
     w = torch.rand((nz, na, nu), device="cuda", generator=g)
     res = {}
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4):
         lib.tmb_fp_set_kernel(mode)
+        lib.tmb_fp_set_segment(24 if mode == 2 else 0)
         try:
             P = ProjTools3D(nu, 0, nz, _angles(na), 0.5, n, "gpu", 0, os_n)
             sub = None if os_n is None else os_n - 1
@@ -179,6 +184,9 @@ def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
             res[mode] = (fp, P.grad_data_term(vol, b, sub, "PWLS", w), P.grad_data_term(vol, b.abs(), sub, "KL"))
         finally:
             lib.tmb_fp_set_kernel(0)
-    for mode in (2, 3):
+            lib.tmb_fp_set_segment(0)
+    for mode in (3, 4):
         for a, c in zip(res[1], res[mode]):
             assert torch.equal(a, c)
+    for a, c in zip(res[1][:2], res[2][:2]):
+        assert rel_max(c.cpu().numpy(), a.cpu().numpy()) < 2e-6

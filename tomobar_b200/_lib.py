@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtmb.so")
+# TMB_LIB selects another build of the same library (A/B timing of kernel changes on one GPU box)
+LIB_PATH = os.environ.get("TMB_LIB") or os.path.join(_HERE, "libtmb.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -31,6 +32,7 @@ SIGNATURES = {
     "tmb_geom_table": (_i, [_vp, C.POINTER(C.c_float)]),
     "tmb_geom_workspace_bytes": (_sz, [_vp]),
     "tmb_fp_set_kernel": (_i, [_i]),
+    "tmb_fp_set_segment": (_i, [_i]),
     "tmb_fp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_bp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_grad": (_i, [_vp, _i, _i, _fp, _fp, _fp, _fp, _vp, _vp]),
@@ -61,6 +63,8 @@ SIGNATURES = {
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
+    if os.environ.get("TMB_LIB") and not hasattr(lib, _name):
+        continue  # an older build loaded for A/B timing may lack newer entry points
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args

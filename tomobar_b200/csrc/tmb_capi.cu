@@ -10,23 +10,29 @@ namespace tmb {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int subset_size(const tmb_geom *g, int subset);
-extern int g_fpq_single;
+extern int g_fpq_mode;
 static std::atomic<uint64_t> g_next_id{1};
 // test hook: which forward-projector kernel geometries created from now on use
 // (0 = by stack height, 1 = k_fp, 2 = k_fpq)
 static int g_fp_kernel = 0;
+static int g_fp_segment = 0;  // test hook: forced k_fpq segment length in lines (0 = sized for L2)
 }  // namespace tmb
 
 using namespace tmb;
 
 extern "C" int tmb_version(void) { return 100; }
 extern "C" int tmb_fp_set_kernel(int mode) {
-  const int old = g_fp_kernel + (g_fpq_single ? 1 : 0);
-  g_fp_kernel = (mode == 1) ? 1 : ((mode == 2 || mode == 3) ? 2 : 0);
-  g_fpq_single = mode == 3;
+  const int old = g_fp_kernel == 2 ? g_fpq_mode : g_fp_kernel;
+  g_fp_kernel = (mode == 1) ? 1 : ((mode >= 2 && mode <= 4) ? 2 : 0);
+  g_fpq_mode = (mode >= 2 && mode <= 4) ? mode : 0;
   return old;
 }
 extern "C" const char *tmb_last_error(void) { return g_err.c_str(); }
+extern "C" int tmb_fp_set_segment(int lines) {
+  const int old = g_fp_segment;
+  g_fp_segment = lines > 0 ? lines : 0;
+  return old;
+}
 
 // Per-angle fp32 table derived in double from the parallel3d_vec vectors of
 // supp/funcs.py:45-81: ray (sin, -cos, 0), detector centre CoR*(cos, sin, 0), u (cos, sin, 0).
@@ -82,7 +88,29 @@ extern "C" tmb_geom *tmb_geom_create(int nz, int n, int nu, int na, const double
   g->off_v0 = 0;
   g->off_v1 = al(vbytes);
   g->off_s = g->off_v1 + al(vbytes);
-  g->ws_bytes = g->off_s + al(sbytes);
+  g->off_part = g->off_s + al(sbytes);
+  // k_fpq line segments: both marching directions of one segment of one z-group fit ~48 MB of L2
+  g->seg_len = n; g->nseg = 1; g->part_angles = 0;
+  size_t pbytes = 0;
+  if (g->fp_q) {
+    const double seg_bytes_per_line = 2.0 * g->d.qpq * FQ_CG * sizeof(float4);
+    int sl = g_fp_segment > 0 ? g_fp_segment : (int)(48.0e6 / seg_bytes_per_line);
+    sl = sl < 24 ? 24 : sl;
+    sl -= sl % 3;  // multiple of the lines per pipeline stage
+    if (sl < n) {
+      g->seg_len = sl;
+      g->nseg = (n + sl - 1) / sl;
+      const int tiles = (nu + FQ_K - 1) / FQ_K;
+      const size_t per_angle = sizeof(float4) * (size_t)g->nseg * g->d.nzg * FQ_CG * tiles * FQ_K;
+      const int sub_max = (na + os_number - 1) / os_number;
+      size_t cap = (size_t)1 << 31;  // 2 GiB of partial sums at most
+      int pa = (int)(cap / per_angle);
+      pa = pa < 1 ? 1 : (pa > sub_max ? sub_max : pa);
+      g->part_angles = pa;
+      pbytes = per_angle * pa;
+    }
+  }
+  g->ws_bytes = g->off_part + al(pbytes);
   return g;
 }
 

@@ -136,5 +136,7 @@ struct tmb_geom {
   uint64_t id;              // identity for the constant-memory cache
   int fp_q;                 // 1: forward projector runs on the Q layouts (k_fpq), 0: k_fp
   // workspace carve-up (bytes offsets)
-  size_t off_v0, off_v1, off_s, ws_bytes;
+  size_t off_v0, off_v1, off_s, off_part, ws_bytes;
+  int seg_len, nseg;        // k_fpq: volume lines per L2 segment, number of segments
+  int part_angles;          // angles per launch the partial-sum buffer holds
 };

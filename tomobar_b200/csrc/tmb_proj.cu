@@ -271,6 +271,10 @@ struct FpArgs {
   int n, nu, up, qp, nz, na_loc, na_tot;
   int nzc_alloc;          // z-chunks S_int holds (k_fpq's 32-slice groups may reach past it)
   int zg_first;           // k_fpq: z-group of blockIdx.z == 0
+  // k_fpq line segments (L2 blocking): blockIdx.z = z-group * nseg + segment; a CTA marches
+  // seg_len lines and, when nseg > 1, leaves its raw partial sums in part[seg][zc][angle][nu_pad]
+  int seg_len, nseg, nu_pad, jc;
+  float4 *part;
   int a_first, a_stride;  // constant-table slot of local angle j
   int g_first, g_stride;  // global angle index (row of b / w) of local angle j
   int j_begin;            // local angle of blockIdx.y == 0
@@ -278,6 +282,8 @@ struct FpArgs {
   int fidelity;
   int quant;
 };
+
+__device__ __forceinline__ void fp_epilogue(const FpArgs &p, const float4 &acc, float scale, int j, int k, int zc);
 
 __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
   extern __shared__ __align__(128) unsigned char fp_smem[];
@@ -374,37 +380,41 @@ __global__ void __launch_bounds__(FP_K + 32) k_fp(const FpArgs p) {
 
   if (k >= p.nu) return;
 #pragma unroll
-  for (int c = 0; c < NZC; ++c) {
-    float *a4 = reinterpret_cast<float *>(&acc[c]);
-    if (p.mode == 0) {
+  for (int c = 0; c < NZC; ++c) fp_epilogue(p, acc[c], scale, j, k, zc0 + c);
+}
+
+// Epilogue of the forward projectors for the 4 slices of z-chunk zc of (local angle j, bin k):
+// plain projection into the API layout, or the fused residual (data_fidelities.py:28-39) written
+// directly in the back-projector's layout.  Explicit roundings: identical to the unfused sequence
+// FP -> subtract -> weight.
+__device__ __forceinline__ void fp_epilogue(const FpArgs &p, const float4 &acc, float scale, int j, int k, int zc) {
+  const float *a4 = reinterpret_cast<const float *>(&acc);
+  if (p.mode == 0) {
 #pragma unroll
-      for (int q = 0; q < ZC; ++q) {
-        const int z = (zc0 + c) * ZC + q;
-        if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[q], scale);
-      }
-    } else {
-      // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
-      const int ga = p.g_first + j * p.g_stride;
-      float r[ZC];
-#pragma unroll
-      for (int q = 0; q < ZC; ++q) {
-        const int z = (zc0 + c) * ZC + q;
-        float v = 0.f;
-        if (z < p.nz) {
-          const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
-          // explicit roundings: identical to the unfused sequence FP -> subtract -> weight
-          const float ax = __fmul_rn(a4[q], scale);
-          if (p.fidelity == TMB_FID_KL) {
-            v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
-          } else {
-            v = __fsub_rn(ax, p.b[idx]);
-            if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
-          }
-        }
-        r[q] = v;
-      }
-      p.sint[((size_t)(zc0 + c) * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
+    for (int e = 0; e < ZC; ++e) {
+      const int z = zc * ZC + e;
+      if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[e], scale);
     }
+  } else if (zc < p.nzc_alloc) {
+    const int ga = p.g_first + j * p.g_stride;
+    float r[ZC];
+#pragma unroll
+    for (int e = 0; e < ZC; ++e) {
+      const int z = zc * ZC + e;
+      float v = 0.f;
+      if (z < p.nz) {
+        const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
+        const float ax = __fmul_rn(a4[e], scale);
+        if (p.fidelity == TMB_FID_KL) {
+          v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
+        } else {
+          v = __fsub_rn(ax, p.b[idx]);
+          if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
+        }
+      }
+      r[e] = v;
+    }
+    p.sint[((size_t)zc * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -477,7 +487,9 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, NG == 1 ? 2 : 1) k_fpq(const 
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * FQ_K;
   const int j = p.j_begin + blockIdx.y;  // local angle
-  const int zg0 = p.zg_first + blockIdx.z * NG;
+  const int seg = (int)blockIdx.z % p.nseg;
+  const int zg0 = p.zg_first + ((int)blockIdx.z / p.nseg) * NG;
+  const int m_lo = seg * p.seg_len, m_hi = min(p.n, m_lo + p.seg_len);  // this CTA's volume lines
   const float4 t = c_fp[p.a_first + j * p.a_stride];
   const float alpha = t.x, b0 = t.y, bstep = t.z;
   const float scale = fabsf(t.w);
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, NG == 1 ? 2 : 1) k_fpq(const 
   }
   __syncthreads();
 
-  const int n_iter = (p.n + G - 1) / G;
+  const int n_iter = (m_hi - m_lo + G - 1) / G;
   const int win = min(FQ_W, (int)ceilf((float)(FQ_K - 1) * fabsf(bstep)) + 4);
 
   if (tid >= FQ_THREADS) {
@@ -506,8 +518,8 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, NG == 1 ? 2 : 1) k_fpq(const 
         const int s = it % FQ_STAGES;
         const uint32_t ph = (it / FQ_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const int m0 = it * G;
-        const int ng = min(G, p.n - m0);
+        const int m0 = m_lo + it * G;
+        const int ng = min(G, m_hi - m0);
         for (int gm = 0; gm < ng; ++gm) {
           const float xm = (float)(m0 + gm) - half + 0.5f;
           int ws = (int)floorf(fmaf(alpha, xm, beta_min)) - 1;
@@ -542,8 +554,8 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, NG == 1 ? 2 : 1) k_fpq(const 
     const int s = it % FQ_STAGES;
     const uint32_t ph = (it / FQ_STAGES) & 1;
     mbar_wait(&full_bar[s], ph);
-    const int m0 = it * G;
-    const int ng = min(G, p.n - m0);
+    const int m0 = m_lo + it * G;
+    const int ng = min(G, m_hi - m0);
     // (float)(m0 + gm) - half + 0.5f: integers and halves below 2^24 are exact, so base + gm is identical
     const float xbase = (float)m0 - half + 0.5f;
     const float4 *sbuf = &buf[s][0][0][0][cc];
@@ -569,40 +581,32 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, NG == 1 ? 2 : 1) k_fpq(const 
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
 
-  if (k >= p.nu) return;
 #pragma unroll
   for (int q = 0; q < NG; ++q) {
     const int zc = (zg0 + q) * FQ_CG + cc;
-    float *a4 = reinterpret_cast<float *>(&acc[q]);
-    if (p.mode == 0) {
-#pragma unroll
-      for (int e = 0; e < ZC; ++e) {
-        const int z = zc * ZC + e;
-        if (z < p.nz) p.sino[((size_t)z * p.na_loc + j) * p.nu + k] = __fmul_rn(a4[e], scale);
-      }
-    } else if (zc < p.nzc_alloc) {
-      // fused residual (data_fidelities.py:28-39) written directly in the back-projector's layout
-      const int ga = p.g_first + j * p.g_stride;
-      float r[ZC];
-#pragma unroll
-      for (int e = 0; e < ZC; ++e) {
-        const int z = zc * ZC + e;
-        float v = 0.f;
-        if (z < p.nz) {
-          const size_t idx = ((size_t)z * p.na_tot + ga) * p.nu + k;
-          const float ax = __fmul_rn(a4[e], scale);
-          if (p.fidelity == TMB_FID_KL) {
-            v = __fsub_rn(1.0f, __fdiv_rn(p.b[idx], fmaxf(ax, 1e-8f)));
-          } else {
-            v = __fsub_rn(ax, p.b[idx]);
-            if (p.w != nullptr) v = __fmul_rn(v, p.w[idx]);
-          }
-        }
-        r[e] = v;
-      }
-      p.sint[((size_t)zc * p.na_loc + j) * p.up + SPAD + k] = make_float4(r[0], r[1], r[2], r[3]);
+    if (p.part != nullptr) {
+      // raw partial sum of this line segment; k_fp_finish adds the segments up in a fixed order
+      const int nzc8 = (int)(gridDim.z / p.nseg) * NG * FQ_CG + p.zg_first * FQ_CG;
+      p.part[(((size_t)seg * nzc8 + zc) * p.jc + blockIdx.y) * p.nu_pad + k] = acc[q];
+    } else if (k < p.nu) {
+      fp_epilogue(p, acc[q], scale, j, k, zc);
     }
   }
+}
+
+// adds up the line-segment partial sums of k_fpq (fixed order: deterministic) and applies the epilogue
+__global__ void k_fp_finish(const FpArgs p, int nzc8) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jl = blockIdx.y, zc = blockIdx.z;
+  if (k >= p.nu) return;
+  const int j = p.j_begin + jl;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sg = 0; sg < p.nseg; ++sg) {
+    const float4 v = p.part[(((size_t)sg * nzc8 + zc) * p.jc + jl) * p.nu_pad + k];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float scale = fabsf(c_fp[p.a_first + j * p.a_stride].w);
+  fp_epilogue(p, acc, scale, j, k, zc);
 }
 
 // ==========================================================================================
@@ -692,8 +696,9 @@ __global__ void k_resid_post(const PostArgs p) {
 // ==========================================================================================
 // host-side launchers
 // ==========================================================================================
-// test hook (tmb_fp_set_kernel(3)): run the Q path with one z-group per CTA only
-int g_fpq_single = 0;
+// test hook (tmb_fp_set_kernel): 0 / 2 = k_fpq<1> with line segments, 3 = k_fpq<2> (two z-groups per
+// CTA, no segments), 4 = k_fpq<1> without segments
+int g_fpq_mode = 0;
 static int subset_first(const tmb_geom *g, int subset) { return subset < 0 ? 0 : subset; }
 static int subset_stride(const tmb_geom *g, int subset) { return subset < 0 ? 1 : g->os_number; }
 int subset_size(const tmb_geom *g, int subset) {
@@ -780,17 +785,38 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
     a.j_begin = j;
     // grid.y is limited to 65535: far above any angle count
     if (g->fp_q) {
-      // pairs of z-groups per CTA, a last odd group on its own
-      const int pairs = g_fpq_single ? 0 : g->d.nzg / 2;
-      if (pairs > 0) {
+      const int tiles = (g->d.nu + FQ_K - 1) / FQ_K;
+      a.seg_len = g->seg_len; a.nseg = g->nseg; a.nu_pad = tiles * FQ_K;
+      if (g_fpq_mode == 3) {
+        // experiment: two z-groups per CTA (8 slices per thread), no line segments
+        a.nseg = 1; a.seg_len = g->d.n; a.part = nullptr; a.jc = cnt;
+        const int pairs = g->d.nzg / 2;
+        if (pairs > 0) {
+          a.zg_first = 0;
+          k_fpq<2><<<dim3(tiles, cnt, pairs), FQ_THREADS + 32, smem_q2, st>>>(a);
+        }
+        if (g->d.nzg - 2 * pairs > 0) {
+          a.zg_first = 2 * pairs;
+          k_fpq<1><<<dim3(tiles, cnt, g->d.nzg - 2 * pairs), FQ_THREADS + 32, smem_q1, st>>>(a);
+        }
+      } else if (g->nseg == 1 || g_fpq_mode == 4) {
+        a.nseg = 1; a.seg_len = g->d.n; a.part = nullptr; a.jc = cnt; a.zg_first = 0;
+        k_fpq<1><<<dim3(tiles, cnt, g->d.nzg), FQ_THREADS + 32, smem_q1, st>>>(a);
+      } else {
+        // L2 blocking: every (bin tile, angle) CTA of one (z-group, line segment) runs back to back,
+        // so a segment (<= ~48 MB for both marching directions) is fetched from HBM once per angle
+        // chunk; the angle chunk is what the partial-sum buffer holds
+        const int nzc8 = g->d.nzg * FQ_CG;
         a.zg_first = 0;
-        dim3 gridq((g->d.nu + FQ_K - 1) / FQ_K, cnt, pairs);
-        k_fpq<2><<<gridq, FQ_THREADS + 32, smem_q2, st>>>(a);
-      }
-      if (g->d.nzg - 2 * pairs > 0) {
-        a.zg_first = 2 * pairs;
-        dim3 gridq((g->d.nu + FQ_K - 1) / FQ_K, cnt, g->d.nzg - 2 * pairs);
-        k_fpq<1><<<gridq, FQ_THREADS + 32, smem_q1, st>>>(a);
+        a.part = reinterpret_cast<float4 *>(const_cast<char *>(reinterpret_cast<const char *>(v0)) - g->off_v0 +
+                                            g->off_part);
+        for (int c0 = 0; c0 < cnt; c0 += g->part_angles) {
+          const int jc = min(g->part_angles, cnt - c0);
+          a.j_begin = j + c0; a.jc = jc;
+          k_fpq<1><<<dim3(tiles, jc, g->d.nzg * g->nseg), FQ_THREADS + 32, smem_q1, st>>>(a);
+          k_fp_finish<<<dim3((g->d.nu + 127) / 128, jc, nzc8), 128, 0, st>>>(a, nzc8);
+        }
+        a.j_begin = j;
       }
     } else {
       dim3 grid((g->d.nu + FP_K - 1) / FP_K, cnt, g->d.nzc / NZC);

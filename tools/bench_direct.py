@@ -41,7 +41,7 @@ def main():
     vol = torch.rand((nz, n, n), device="cuda", generator=g)
     from tomobar_b200._lib import lib
 
-    for mode, name in ((0, "default"), (1, "k_fp"), (3, "k_fpq<1>"), (2, "k_fpq<2>")):
+    for mode, name in ((0, "default"), (1, "k_fp"), (4, "k_fpq<1>"), (3, "k_fpq<2>"), (2, "k_fpq seg")):
         lib.tmb_fp_set_kernel(mode)
         try:
             Rm = RecToolsDIRCuPy(n, 0, nz, 0.0, angles, n, device_projector=0)
