@@ -242,6 +242,9 @@ def main():
     ap.add_argument("--halo-messages", action="store_true",
                     help="multi-GPU: refresh the TV ghost planes with NCCL send/recv instead of letting the "
                          "kernel read the neighbours' planes over NVLink (peer memory)")
+    ap.add_argument("--halo-barrier", action="store_true",
+                    help="multi-GPU peer-memory halos: one all-rank barrier per TV iteration instead of "
+                         "pairwise semaphores with the two neighbours")
     ap.add_argument("--independent-tv", action="store_true",
                     help="multi-GPU: TV per z-shard without halo exchange (seams at the shard borders)")
     args = ap.parse_args()
@@ -249,7 +252,8 @@ def main():
                tv_lambda=HEADLINE["tv_lambda"], algo=args.algo,
                halo=("independent z-blocks" if args.independent_tv else
                      "exact, NCCL messages between inner iterations" if args.halo_messages else
-                     "exact, peer loads over NVLink inside the TV kernel"))
+                     "exact, peer loads over NVLink inside the TV kernel"
+                     + (", all-rank barrier per iteration" if args.halo_barrier else ", pairwise semaphores")))
     if args.warmup < 3:
         args.warmup = 3
 
@@ -285,6 +289,7 @@ def main():
     if world > 1 and not args.independent_tv:
         rec.set_zshard(shard)
         rec.tv_peer_memory = False if args.halo_messages else None
+        rec.tv_sync = "barrier" if args.halo_barrier else "signals"
     rec.nonneg_regul = 1
     A = rec.Atools
     # synthetic data generated on the device, slice blocks of 16 to bound temporaries
@@ -398,10 +403,21 @@ def main():
     peak, peak_src = measured_peak_hbm()
     tv_gbs = bytes_tv / (ms_tv * 1e-3) / 1e9
     share_tv = ms_tv * (30 if admm else cfg["tv_iters"]) / ms_step
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this very
+    # launch shape (profiles/ncu_traffic_r01.json: dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
+            for rec_t in json.load(fh):
+                if (rec_t["kernel"] == ("k_rof_tv3d_w" if admm else "k_pd_tv3d_w") and rec_t["voxels"] == count
+                        and bool(rec_t.get("half", False)) == bool(args.half)):
+                    traffic = float(rec_t["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roofline = {
         "kernel": ("k_rof_tv3d_w (one fused ROF iteration; instruction-bound, 12 B/voxel)" if admm else
                    "k_pd_tv3d_w (one Chambolle-Pock iteration, warp-strip kernel)"), "bound": "hbm", "achieved": tv_gbs, "peak": peak,
-        "unit": "GB/s", "frac": tv_gbs / peak, "peak_source": peak_src, "traffic": None,
+        "unit": "GB/s", "frac": tv_gbs / peak, "peak_source": peak_src, "traffic": traffic,
         "algorithmic_bytes_per_launch": bytes_tv, "ms_per_launch": ms_tv, "share_of_step": share_tv,
     }
     kernels = {

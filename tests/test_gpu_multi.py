@@ -32,14 +32,15 @@ def _worker(rank, world, init_file, results):
         out = {}
         # --- sharded PD_TV prox == whole-volume prox, bit for bit --------------------------------
         out["tv_equal_half0"] = out["tv_equal_half1"] = out["rof_equal"] = True
-        for peer in (True, False):  # halos read over NVLink inside the kernel / sent as messages
+        for peer, sync in ((True, "signals"), (True, "barrier"), (False, "signals")):
+            # halos read over NVLink inside the kernel (two ways of ordering the iterations) / sent as messages
             for half in (False, True):
-                tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half, peer_memory=peer)
+                tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half, peer_memory=peer, sync=sync)
                 whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
                 for _ in range(2):  # buffers are reused across calls
                     part = tv(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0)
                     out[f"tv_equal_half{int(half)}"] &= bool(torch.equal(sh.all_gather_volume(part), whole))
-            rof = ShardedROFTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=peer)
+            rof = ShardedROFTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=peer, sync=sync)
             part = rof(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 1e-3)
             out["rof_equal"] &= bool(torch.equal(sh.all_gather_volume(part),
                                                  ROF_TV_cupy(full, 4e-4, 9, 1e-3, rank, False)))
@@ -70,16 +71,20 @@ def _worker(rank, world, init_file, results):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_tv_and_fista():
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_sharded_tv_and_fista(world):
+    """world = 4 has interior ranks (two neighbours each), world = 2 only boundary ranks."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     with tempfile.TemporaryDirectory() as d:
         mgr = mp.Manager()
         results = mgr.dict()
-        mp.spawn(_worker, args=(2, os.path.join(d, "rdzv"), results), nprocs=2, join=True)
-    for r in range(2):
+        mp.spawn(_worker, args=(world, os.path.join(d, "rdzv"), results), nprocs=world, join=True)
+    for r in range(world):
         res = results[r]
         assert res["tv_equal_half0"] and res["tv_equal_half1"], res
         assert res["rof_equal"], res
         assert res["fista_equal"], res
         assert res["admm_equal"], res
         assert res["L_sharded"] == pytest.approx(res["L_whole"], rel=1e-3)
-    assert results[0]["L_sharded"] == results[1]["L_sharded"]
+    assert all(results[r]["L_sharded"] == results[0]["L_sharded"] for r in range(world))

@@ -86,6 +86,7 @@ class RecToolsIRCuPy:
         self.power_seed = 0  # the reference draws an unseeded cp.random.randn (:326)
         self.zshard = None   # set_zshard(): this object reconstructs one z-block of a larger volume
         self.tv_peer_memory = None  # sharded TV halos: None = NVLink peer loads on NCCL, False = messages
+        self.tv_sync = "signals"    # peer-memory ordering: pairwise semaphores, or "barrier"
         self._sharded_tv = {}
 
     def set_zshard(self, shard) -> None:
@@ -276,7 +277,7 @@ class RecToolsIRCuPy:
 
                 key = ("rof", tuple(X.shape), bool(reg.get("half_precision", False)))
                 if key not in self._sharded_tv:
-                    self._sharded_tv = {key: ShardedROFTV(sh, key[1], X.device, key[2], self.tv_peer_memory)}
+                    self._sharded_tv = {key: ShardedROFTV(sh, key[1], X.device, key[2], self.tv_peer_memory, self.tv_sync)}
                 return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["time_marching_step"],
                                              out=out)
             return ROF_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["time_marching_step"], dev,
@@ -288,7 +289,7 @@ class RecToolsIRCuPy:
 
                 key = ("pd", tuple(X.shape), bool(reg.get("half_precision", False)))
                 if key not in self._sharded_tv:
-                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2], self.tv_peer_memory)}
+                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2], self.tv_peer_memory, self.tv_sync)}
                 return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["methodTV"],
                                              self.nonneg_regul, reg["PD_LipschitzConstant"], out=out)
             return PD_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["methodTV"], self.nonneg_regul,

@@ -147,6 +147,44 @@ class _PeerSlab:
         """Cross-GPU barrier on the current stream (signal pads in peer memory)."""
         self.hdl.barrier(0)
 
+    # pairwise stream-ordered semaphores (one per ordered pair of ranks and channel)
+    def signal(self, peers) -> None:
+        for r in peers:
+            self.hdl.put_signal(int(r), 1)
+
+    def wait(self, peers) -> None:
+        for r in peers:
+            self.hdl.wait_signal(int(r), 1)
+
+
+class _NeighbourSync:
+    """Ordering of the peer-memory TV iterations.  Before a rank launches iteration k it needs its two
+    neighbours to have finished iteration k - 1 (they wrote the planes it is about to read and read the
+    planes it is about to overwrite).  ``mode="signals"``: pairwise semaphores with the two neighbours
+    (a put after every kernel, a wait before the next one); ``mode="barrier"``: one barrier over all
+    ranks per iteration."""
+
+    def __init__(self, slab: _PeerSlab, shard: "ZShard", mode: str):
+        if mode not in ("signals", "barrier"):
+            raise ValueError("sync mode must be 'signals' or 'barrier'")
+        self.slab, self.mode = slab, mode
+        self.peers = [shard._global(r) for r in (shard.prev, shard.next) if r is not None]
+        self.pending = False  # neighbours have signalled the end of their previous work
+
+    def produced(self) -> None:
+        """This rank's buffers are ready for the neighbours / it no longer reads theirs."""
+        if self.mode == "signals":
+            self.slab.signal(self.peers)
+            self.pending = True
+
+    def acquire(self) -> None:
+        """Wait until the neighbours have done the same."""
+        if self.mode == "barrier":
+            self.slab.barrier()
+        elif self.pending:
+            self.slab.wait(self.peers)
+            self.pending = False
+
 
 def _peer_memory_default(shard: "ZShard", device: torch.device) -> bool:
     return shard.world > 1 and device.type == "cuda" and dist.get_backend(shard.group) == "nccl"
@@ -168,7 +206,7 @@ class ShardedPDTV:
     Buffers are allocated once and reused across calls."""
 
     def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False,
-                 peer_memory: Optional[bool] = None):
+                 peer_memory: Optional[bool] = None, sync: str = "signals"):
         nzl, ny, nx = shape
         if nzl != shard.nz_local:
             raise ValueError("ShardedPDTV: the volume shard does not match the z-partition")
@@ -187,6 +225,8 @@ class ShardedPDTV:
         self._plane, self._esz = plane, esz
         self.slab = _PeerSlab(2 * self._ub + 6 * self._pb, device, shard.group)
         self.slab.buf.zero_()
+        self.slab.barrier()
+        self.sync = _NeighbourSync(self.slab, shard, sync)
         self.U = [self.slab.view(a * self._ub, (nzl + 2, ny, nx), torch.float32) for a in range(2)]
         self.P = [[self.slab.view(2 * self._ub + (a * 3 + c) * self._pb, (nzl + 1, ny, nx), pdt) for c in range(3)]
                   for a in range(2)]
@@ -216,19 +256,22 @@ class ShardedPDTV:
             raise ValueError(f"ShardedPDTV: expected a contiguous float32 volume shard of shape {self.shape}")
         U, P = self.U, self.P
         if self.peer:
-            self.slab.barrier()  # nobody still reads the buffers of the previous call
+            self.sync.acquire()  # nobody still reads the buffers of the previous call
         U[0][1:nzl + 1].copy_(data)
         for c in range(3):
             P[0][c].zero_()
+        if self.peer:
+            self.sync.produced()
         ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
         with torch.cuda.device(self.device):
             for it in range(int(iterations)):
                 a, b = it % 2, 1 - it % 2
                 u_lo = p_lo = u_hi = None
                 if self.peer:
-                    # every rank has finished writing set `a` (and reading set `b`): one barrier per
-                    # iteration replaces the halo messages, the kernel loads the planes over NVLink
-                    self.slab.barrier()
+                    # the neighbours have finished writing set `a` (and reading set `b`): a pairwise
+                    # semaphore (or one barrier) per iteration replaces the halo messages, the kernel
+                    # loads the planes over NVLink
+                    self.sync.acquire()
                     u_lo, p_lo, u_hi = self._ghost_ptrs(a)
                 else:
                     up = [(U[a][nzl], U[a][0])]
@@ -241,6 +284,8 @@ class ShardedPDTV:
                                          nzl, ny, nx, float(regularisation_parameter), int(methodTV), int(nonneg),
                                          float(lipschitz_const), int(self.half), ghost_lo, ghost_hi,
                                          u_lo, p_lo[0], p_lo[1], p_lo[2], u_hi, stream_ptr(data)), "tmb_pd_tv_iter")
+                if self.peer:
+                    self.sync.produced()
         res = U[int(iterations) % 2][1:nzl + 1]
         if out is None:
             return res.clone()
@@ -258,7 +303,7 @@ class ShardedROFTV:
     (top two planes to the next rank, bottom plane to the previous one)."""
 
     def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False,
-                 peer_memory: Optional[bool] = None):
+                 peer_memory: Optional[bool] = None, sync: str = "signals"):
         nzl, ny, nx = shape
         if nzl != shard.nz_local:
             raise ValueError("ShardedROFTV: the volume shard does not match the z-partition")
@@ -274,6 +319,8 @@ class ShardedROFTV:
         self._ub = (per + 3) * self._plane * 4
         self.slab = _PeerSlab(2 * self._ub, device, shard.group)
         self.slab.buf.zero_()
+        self.slab.barrier()
+        self.sync = _NeighbourSync(self.slab, shard, sync)
         self.U = [self.slab.view(a * self._ub, (nzl + 3, ny, nx), torch.float32) for a in range(2)]
 
     def _ghost_ptrs(self, a: int):
@@ -298,15 +345,17 @@ class ShardedROFTV:
             raise ValueError(f"ShardedROFTV: expected a contiguous float32 volume shard of shape {self.shape}")
         U = self.U
         if self.peer:
-            self.slab.barrier()
+            self.sync.acquire()
         U[0][2:nzl + 2].copy_(data)
+        if self.peer:
+            self.sync.produced()
         ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
         with torch.cuda.device(self.device):
             for it in range(int(iterations)):
                 a, b = it % 2, 1 - it % 2
                 u_lo = u_hi = None
                 if self.peer:
-                    self.slab.barrier()
+                    self.sync.acquire()
                     u_lo, u_hi = self._ghost_ptrs(a)
                 else:
                     sh.exchange_halos([(U[a][nzl:nzl + 2], U[a][0:2])], [(U[a][2], U[a][nzl + 2])])
@@ -314,6 +363,8 @@ class ShardedROFTV:
                                           float(regularisation_parameter), float(time_marching_parameter),
                                           int(self.half), ghost_lo, ghost_hi, u_lo, u_hi, stream_ptr(data)),
                           "tmb_rof_tv_iter")
+                if self.peer:
+                    self.sync.produced()
         res = U[int(iterations) % 2][2:nzl + 2]
         if out is None:
             return res.clone()
