@@ -460,7 +460,8 @@ def main():
             dt = float(tt.item())
         e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": int(b_host.numel() * 4 / os_n),
                "d2h_bytes_per_step": int(out_host.numel() * 4 / os_n),
-               "note": "RecToolsIRCuPy.FISTA(iterations=1) from pinned host sinogram to pinned host volume"}
+               "note": f"RecToolsIRCuPy.{'ADMM' if admm else 'FISTA'}(iterations=1) from pinned host sinogram to "
+                       "pinned host volume"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
