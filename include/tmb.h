@@ -169,6 +169,9 @@ int tmb_axpy(float a, const float *x, float *y, size_t count, int nonneg, void *
 int tmb_sinc_filter(float cutoff, float *f, int n, float multiplier, void *stream);
 /* spectrum *= filter, in place; spec is interleaved complex64 [rows][n/2+1] (fourier.py:69)    */
 int tmb_apply_filter(float *spec, const float *f, size_t rows, int nbins, void *stream);
+/* edge padding of the detector axis (supp/suppTools.py:425-459 _apply_horiz_detector_padding;
+ * methodsDIR_CuPy.py:505-521): out[rows][wout], out[r][j] = in[r][clamp(j - pad_left, 0, w - 1)]   */
+int tmb_edge_pad(const float *in, float *out, size_t rows, int w, int wout, int pad_left, void *stream);
 /* circular mask (supp/suppTools.py:364-396), in place on vol[nz][n][n]                        */
 int tmb_circular_mask(float *vol, int nz, int n, float radius, void *stream);
 
@@ -182,13 +185,15 @@ int tmb_normalise(const void *data, int data_is_u16, const float *flat_mean, con
  * Replace the default centre-gather path of RecToolsDIRCuPy.FOURIER_INV (methodsDIR_CuPy.py:152-447)
  * and cuda_kernels/fft_us_kernels.cu; the FFTs themselves are cuFFT calls made by the host.
  * Complex arrays are interleaved float pairs.  nz2 = number of complex slices (= slices / 2).
- *   tmb_fi_pack       : tmp_p[2*nz2][nproj][n] -> datac[nz2][nproj][n], x (-1)^(x+1)   (r2c_c1dfftshift :529-557)
- *   tmb_fi_scale_sign : datac *= c * (-1)^(x+1)                                        (c1dfftshift :559-586)
- *   tmb_fi_gather     : polar samples -> fde[nz2][2n][2n]; theta = -angles (device), sorted_theta /
- *                       sorted_idx = ascending sort of theta and its permutation (int32)
- *                       (gather_kernel_center_angle_based_prune :193-319 + gather_kernel_center :468-527)
- *   tmb_fi_sign2d     : fde *= (-1)^(x+y)                                              (c2dfftshift :588-609)
- *   tmb_fi_unpad      : crop, de-apodise, unpack re/im -> recon[unpad_z][R][R]         (unpadding_mul_phi :611-657) */
+ *   tmb_fi_pack         : tmp_p[2*nz2][nproj][n] -> datac[nz2][nproj][n], x (-1)^(x+1)  (r2c_c1dfftshift :529-557)
+ *   tmb_fi_scale_sign   : datac *= c * (-1)^(x+1), in place                              (c1dfftshift :559-586)
+ *   tmb_fi_gather       : polar samples datac -> fde[nz2][2n][2n], ALREADY multiplied by (-1)^(x+y) (the first
+ *                         c2dfftshift of :860-868 is fused); theta = -angles (device), sorted_theta / sorted_idx =
+ *                         ascending sort of theta and its permutation (int32)
+ *                         (gather_kernel_center_angle_based_prune :193-319 + gather_kernel_center :468-527)
+ *   tmb_fi_sign2d       : fde *= (-1)^(x+y)                                              (c2dfftshift :588-609)
+ *   tmb_fi_unpad        : (-1)^(x+y) of the second c2dfftshift (:888-896, fused), crop, de-apodise, unpack re/im
+ *                         -> recon[unpad_z][R][R]                                         (unpadding_mul_phi :611-657) */
 int tmb_fi_pack(const float *tmp_p, float *datac, int n, int nproj, int nz2, void *stream);
 int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
 int tmb_fi_gather(const float *datac, float *fde, const float *theta, const float *sorted_theta,

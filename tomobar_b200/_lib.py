@@ -51,6 +51,7 @@ SIGNATURES = {
     "tmb_axpy": (_i, [_f, _fp, _fp, _sz, _i, _vp]),
     "tmb_sinc_filter": (_i, [_f, _fp, _i, _f, _vp]),
     "tmb_apply_filter": (_i, [_fp, _fp, _sz, _i, _vp]),
+    "tmb_edge_pad": (_i, [_fp, _fp, _sz, _i, _i, _i, _vp]),
     "tmb_circular_mask": (_i, [_fp, _i, _i, _f, _vp]),
     "tmb_normalise": (_i, [_vp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
     "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),

@@ -135,6 +135,18 @@ __global__ void k_apply_filter(float2 *__restrict__ spec, const float *__restric
   }
 }
 
+// edge padding of the last axis (supp/suppTools.py:425-459; methodsDIR_CuPy.py:505-521):
+// out[row][j] = in[row][clamp(j - pad_left, 0, w - 1)]
+__global__ void k_edge_pad(const float *__restrict__ in, float *__restrict__ out, size_t rows, int w, int wout,
+                           int pad_left) {
+  const size_t total = rows * (size_t)wout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / wout;
+    const int j = (int)(i - r * wout) - pad_left;
+    out[i] = __ldg(in + r * w + min(max(j, 0), w - 1));
+  }
+}
+
 // circular mask (supp/suppTools.py:364-396)
 __global__ void k_mask(float *__restrict__ vol, int nz, int n, double limit) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,4 +269,11 @@ extern "C" int tmb_normalise(const void *data, int data_is_u16, const float *fla
     k_normalise<float><<<el_blocks(total), EL_THREADS, 0, (cudaStream_t)stream>>>(
         static_cast<const float *>(data), flat_mean, dark_mean, out, total, n1, n2, angle_axis, take_log);
   return check_launch("k_normalise");
+}
+
+extern "C" int tmb_edge_pad(const float *in, float *out, size_t rows, int w, int wout, int pad_left, void *stream) {
+  TMB_REQUIRE(in && out && in != out && w >= 1 && wout >= w && pad_left >= 0 && pad_left + w <= wout,
+              "tmb_edge_pad: bad argument");
+  k_edge_pad<<<el_blocks(rows * (size_t)wout), EL_THREADS, 0, (cudaStream_t)stream>>>(in, out, rows, w, wout, pad_left);
+  return check_launch("k_edge_pad");
 }

@@ -11,7 +11,7 @@
 // The FFTs themselves run in cuFFT (called by the host through torch.fft).
 //
 // k_fi_gather: one thread owns one point of the 2n x 2n Cartesian frequency grid and a chunk of
-// complex slices.  A polar line (projection) contributes to the point when it passes within
+// FI_SC complex slices (the loads of a warp are coalesced along the radial sample index).  A polar line (projection) contributes to the point when it passes within
 // r = sqrt(2)(m + 1/2)/(2n) of it, i.e. when its angle lies in phi +- asin(r/|p|) (mod pi); the
 // thread finds those index ranges in the sorted angle list by binary search, then, per line,
 // walks the chord inside the disc and accumulates Gaussian-weighted samples.  The Gaussian
@@ -22,7 +22,8 @@
 namespace tmb {
 
 constexpr float FI_PI = 3.14159265358979323846f;
-constexpr int FI_SC = 4;  // complex slices per thread in the gather
+constexpr int FI_SC = 4;  // complex slices per thread in the gather (measured: 4 -> 81 ms, 32 -> 148 ms at config 4:
+                          // more slices per thread cost parallelism and cache locality across 32 planes)
 
 __global__ void k_fi_pack(const float *__restrict__ in, float2 *__restrict__ out, int n, int nproj, int nz2) {
   const int tx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,10 +177,12 @@ __global__ void __launch_bounds__(128)
       done = max(done, hi);
     }
   }
+  // the (-1)^(x+y) of the centred inverse 2-D FFT (c2dfftshift, :588-609) is applied on the way out
+  const float sg = ((tx ^ ty) & 1) ? -1.f : 1.f;
   const size_t o = (size_t)ty * n2 + tx;
 #pragma unroll
   for (int s = 0; s < FI_SC; ++s)
-    if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = acc[s];
+    if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = make_float2(acc[s].x * sg, acc[s].y * sg);
 }
 
 __global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__ f, float mu, int nproj, int up,
@@ -192,7 +195,11 @@ __global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__
   const int n2 = 2 * n;
   const int rs = up - um;
   const size_t rs2 = (size_t)rs * rs;
-  const float2 v = f[(size_t)rz * n2 * n2 + (size_t)(n / 2 + ry) * n2 + (n / 2 + rx)];
+  float2 v = f[(size_t)rz * n2 * n2 + (size_t)(n / 2 + ry) * n2 + (n / 2 + rx)];
+  if (((n / 2 + ry) ^ (n / 2 + rx)) & 1) {  // the second c2dfftshift, fused
+    v.x = -v.x;
+    v.y = -v.y;
+  }
   const float ddx = -0.5f + rx * 1.f / n;
   const float ddy = -0.5f + ry * 1.f / n;
   const float phi = expf(mu * (n * n) * (ddx * ddx + ddy * ddy)) * ((float)(1 - n % 4) / nproj);

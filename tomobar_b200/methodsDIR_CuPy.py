@@ -15,7 +15,7 @@ from tomobar_b200._tensors import as_cuda_f32, ptr, stream_ptr
 from tomobar_b200.fourier import _filtersinc3D_cupy, calc_filter
 from tomobar_b200.projector import ProjTools3D
 from tomobar_b200.supp.funcs import _data_dims_swapper, _parse_device_argument
-from tomobar_b200.supp.suppTools import _apply_horiz_detector_padding, check_kwargs
+from tomobar_b200.supp.suppTools import _apply_horiz_detector_padding, check_kwargs, edge_pad
 
 
 class RecToolsDIRCuPy:
@@ -202,17 +202,16 @@ class RecToolsDIRCuPy:
             datac = torch.fft.fft(datac, dim=-1)
             check(lib.tmb_fi_scale_sign(ptr(datac), float(np.float32(4 / n)), n, nproj, nz2, st), "tmb_fi_scale_sign")
             m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
-            # STEP 2: gather polar samples onto the 2n x 2n Cartesian grid (:781-816)
+            # STEP 2: gather polar samples onto the 2n x 2n Cartesian grid (:781-816); the (-1)^(x+y)
+            # before the 2-D FFT is applied by the gather, the one after it by the unpadding kernel
             fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
             check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
                                     float(np.float32(mu)), n, nproj, nz2, st), "tmb_fi_gather")
             del datac
             # STEP 3: centred 2-D inverse FFT (:851-896)
-            check(lib.tmb_fi_sign2d(ptr(fde), n, nz2, st), "tmb_fi_sign2d")
             chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))  # bound cuFFT workspace
             for s0 in range(0, nz2, chunk):
                 fde[s0:s0 + chunk] = torch.fft.ifft2(fde[s0:s0 + chunk], dim=(-2, -1))
-            check(lib.tmb_fi_sign2d(ptr(fde), n, nz2, st), "tmb_fi_sign2d")
             # STEP 4: crop, de-apodise, unpack the slice pairs (:920-966)
             odd_recon = bool(recon_size % 2)
             unpad_z = nz - odd_vert
@@ -248,10 +247,7 @@ class RecToolsDIRCuPy:
         # slice chunks bound the oversampled temporaries (the reference chunks for the same reason)
         per = max(1, (1 << 27) // (nproj * over))
         for z0 in range(0, nz, per):
-            blk = data[z0:z0 + per]
-            left = blk[..., :1].expand(-1, -1, padding_m)
-            right = blk[..., -1:].expand(-1, -1, padding_m)
-            tmp = torch.cat((left, blk, right), dim=-1)
+            tmp = edge_pad(data[z0:z0 + per], padding_m, raw_width + 2 * padding_m)
             tmp = torch.fft.irfft(w * torch.fft.rfft(tmp, dim=2), n=over, dim=2)
             out[z0:z0 + per] = tmp[:, :, unpad_m:unpad_p]
         return out

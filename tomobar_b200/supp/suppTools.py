@@ -14,10 +14,19 @@ def _apply_horiz_detector_padding(data: torch.Tensor, detector_width_pad: int, c
     """Edge-pad detX (the last axis) on both sides (suppTools.py:425-459)."""
     if detector_width_pad <= 0:
         return data
-    p = int(detector_width_pad)
-    left = data[..., :1].expand(*data.shape[:-1], p)
-    right = data[..., -1:].expand(*data.shape[:-1], p)
-    return torch.cat((left, data, right), dim=-1)
+    return edge_pad(data, int(detector_width_pad), data.shape[-1] + 2 * int(detector_width_pad))
+
+
+def edge_pad(data: torch.Tensor, pad_left: int, width_out: int) -> torch.Tensor:
+    """out[..., j] = data[..., clamp(j - pad_left, 0, w - 1)] in one fused pass (k_edge_pad)."""
+    data = data.contiguous()
+    w = data.shape[-1]
+    out = torch.empty(tuple(data.shape[:-1]) + (int(width_out),), dtype=torch.float32, device=data.device)
+    rows = data.numel() // w
+    with torch.cuda.device(data.device):
+        check(lib.tmb_edge_pad(ptr(data), ptr(out), rows, w, int(width_out), int(pad_left), stream_ptr(data)),
+              "tmb_edge_pad")
+    return out
 
 
 def perform_recon_crop(data: torch.Tensor, croped_size: int) -> torch.Tensor:
