@@ -89,12 +89,15 @@ extern "C" tmb_geom *tmb_geom_create(int nz, int n, int nu, int na, const double
   g->off_v1 = al(vbytes);
   g->off_s = g->off_v1 + al(vbytes);
   g->off_part = g->off_s + al(sbytes);
-  // k_fpq line segments: both marching directions of one segment of one z-group fit ~48 MB of L2
+  // k_fpq line segments: the marching range is cut so that one segment (both marching directions of
+  // one z-group) is ~190 MB.  Measured optimum (profiles/fp_segments_r01.txt): at N = 2048 segments of
+  // 243-324 lines (139-186 MB) give 77-78 ms per 75-angle subset against 92 ms unsegmented and 83 ms
+  // with 81-line (46 MB) segments; at N = 1024 anything from 200 MB up is within 0.5 % of unsegmented.
   g->seg_len = n; g->nseg = 1; g->part_angles = 0;
   size_t pbytes = 0;
   if (g->fp_q) {
     const double seg_bytes_per_line = 2.0 * g->d.qpq * FQ_CG * sizeof(float4);
-    int sl = g_fp_segment > 0 ? g_fp_segment : (int)(48.0e6 / seg_bytes_per_line);
+    int sl = g_fp_segment > 0 ? g_fp_segment : (int)(190.0e6 / seg_bytes_per_line);
     sl = sl < 24 ? 24 : sl;
     sl -= sl % 3;  // multiple of the lines per pipeline stage
     if (sl < n) {
