@@ -348,8 +348,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # our kernels per sub-step: layout conversion, k_fp, k_bp, gradient step, PD_TV iterations, momentum
-    launches_per_step = 1 + 1 + 1 + 1 + (30 if args.algo == "admm" else cfg["tv_iters"]) + 1
+    # our kernels per sub-step: layout conversion, forward projector (k_fpq [+ k_fp_finish] per chunk),
+    # k_bp, gradient / z step, TV iterations, momentum (ADMM: the u update once per outer iteration)
+    fp_launches = max(1, lib.tmb_geom_fp_launches(A._g, 0))
+    launches_per_step = 1 + fp_launches + 1 + 1 + (30 if args.algo == "admm" else cfg["tv_iters"]) + 1
 
     for _ in range(args.warmup):
         substep()

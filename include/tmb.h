@@ -56,6 +56,8 @@ int tmb_geom_subset_size(const tmb_geom *g, int subset);
 int tmb_geom_subset_row(const tmb_geom *g, int subset, int *out_bins /* [ceil(na/os)] */);
 /* the fp32 per-angle table the kernels read from constant memory: out[na][8] (host) */
 int tmb_geom_table(const tmb_geom *g, float *out);
+/* number of kernels the forward projection of `subset` launches (launch accounting of benchmarks) */
+int tmb_geom_fp_launches(const tmb_geom *g, int subset);
 /* bytes of device scratch tmb_fp3d / tmb_bp3d / tmb_grad need.  The caller allocates it ONCE,
  * zero-fills it ONCE (the kernels keep the zero borders intact) and passes it to every call. */
 size_t tmb_geom_workspace_bytes(const tmb_geom *g);

@@ -903,3 +903,21 @@ extern "C" int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float
   if (rc) return rc;
   return launch_bp(g, subset, ws.s, grad, st);
 }
+
+// Number of kernels the forward projection of `subset` launches (k_fp / k_fpq per constant-table and
+// partial-buffer chunk, plus k_fp_finish when the march is segmented): for launch accounting.
+extern "C" int tmb_geom_fp_launches(const tmb_geom *g, int subset) {
+  if (!g || subset < -1 || subset >= g->os_number) return TMB_ERR_ARG;
+  const int na_loc = subset_size(g, subset);
+  const int first = subset < 0 ? 0 : subset, stride = subset < 0 ? 1 : g->os_number;
+  int launches = 0, j = 0;
+  while (j < na_loc) {
+    const int chunk_base = ((first + j * stride) / MAX_ANGLES) * MAX_ANGLES;
+    int cnt = 0;
+    while (j + cnt < na_loc && first + (j + cnt) * stride < chunk_base + MAX_ANGLES) ++cnt;
+    if (g->fp_q && g->nseg > 1) launches += 2 * ((cnt + g->part_angles - 1) / g->part_angles);
+    else launches += 1;
+    j += cnt;
+  }
+  return launches;
+}
