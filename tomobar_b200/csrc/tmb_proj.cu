@@ -434,41 +434,41 @@ constexpr int FQ_G2 = 2;      // ... with two z-groups per CTA (twice the bytes 
 constexpr int FQ_STAGES = 3;
 constexpr int FQ_THREADS = FQ_K * FQ_CG;
 
-// vol[nz][n][n] -> VQ1 / VQ0; a block converts a 32 x 32 in-plane tile of 8 slices (2 chunks)
-__global__ void k_vol_to_intq(const float *__restrict__ vol, float4 *__restrict__ v0, float4 *__restrict__ v1, int nz,
-                              int n, int qpq) {
-  __shared__ float4 tile[2][32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int zc0 = blockIdx.z * 2;  // first of the block's two z-chunks
-  const int zg = zc0 / FQ_CG, cc = zc0 % FQ_CG;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  for (int j = ty; j < 32; j += 8) {
-    const int r = r0 + j, c = c0 + tx;
-    float v[2 * ZC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (r < n && c < n) {
-#pragma unroll
-      for (int k = 0; k < 2 * ZC; ++k) {
-        const int z = zc0 * ZC + k;
-        if (z < nz) v[k] = vol[((size_t)z * n + r) * n + c];
-      }
-    }
-    const float4 q0 = make_float4(v[0], v[1], v[2], v[3]), q1 = make_float4(v[4], v[5], v[6], v[7]);
-    tile[0][j][tx] = q0;
-    tile[1][j][tx] = q1;
-    if (r < n && c < n) {
-      float4 *d = v1 + (((size_t)zg * n + r) * qpq + QPAD + c) * FQ_CG + cc;
-      d[0] = q0;
-      d[1] = q1;
-    }
+// vol[nz][n][n] -> VQ1 / VQ0.  A block converts a 32 (columns) x 8 (rows) in-plane tile of one whole
+// z-group (32 slices): reads are 128-byte rows of the volume, and each position of the Q layouts --
+// 8 chunks x 16 B = one 128-byte line -- is written by 8 consecutive lanes, so every store
+// instruction of a warp fills four whole lines.
+__global__ void __launch_bounds__(256) k_vol_to_intq(const float *__restrict__ vol, float4 *__restrict__ v0,
+                                                      float4 *__restrict__ v1, int nz, int n, int qpq) {
+  // [slice][row][column]; the slice stride is odd so that the 8 chunks x 4 positions a warp writes at
+  // a time read 32 different banks
+  constexpr int TS = 8 * 33 + 1;
+  __shared__ float tile[FQ_CG * ZC * TS];
+  auto T = [&](int zz, int rr, int cl) -> float & { return tile[zz * TS + rr * 33 + cl]; };
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 8, zg = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;  // 8 warps
+  // load: warp w takes row r0 + w of every slice of the group
+  for (int zz = 0; zz < FQ_CG * ZC; ++zz) {
+    const int z = zg * FQ_CG * ZC + zz, r = r0 + w, c = c0 + lane;
+    T(zz, w, lane) = (z < nz && r < n && c < n) ? vol[((size_t)z * n + r) * n + c] : 0.f;
   }
   __syncthreads();
-  for (int j = ty; j < 32; j += 8) {
-    const int c = c0 + j, r = r0 + tx;
-    if (r < n && c < n) {
-      float4 *d = v0 + (((size_t)zg * n + c) * qpq + QPAD + r) * FQ_CG + cc;
-      d[0] = tile[0][tx][j];
-      d[1] = tile[1][tx][j];
-    }
+  const int cc = tid & (FQ_CG - 1);  // chunk written by this thread
+  // VQ1[zg][r][QPAD + c][cc]: positions run along the columns
+  for (int i = tid >> 3; i < 32 * 8; i += 32) {  // i = row * 32 + column
+    const int rr = i >> 5, cl = i & 31;
+    const int r = r0 + rr, c = c0 + cl;
+    if (r < n && c < n)
+      v1[(((size_t)zg * n + r) * qpq + QPAD + c) * FQ_CG + cc] =
+          make_float4(T(cc * ZC, rr, cl), T(cc * ZC + 1, rr, cl), T(cc * ZC + 2, rr, cl), T(cc * ZC + 3, rr, cl));
+  }
+  // VQ0[zg][c][QPAD + r][cc]: positions run along the rows (8 consecutive rows = 1 KB per column)
+  for (int i = tid >> 3; i < 32 * 8; i += 32) {  // i = column * 8 + row
+    const int cl = i >> 3, rr = i & 7;
+    const int r = r0 + rr, c = c0 + cl;
+    if (r < n && c < n)
+      v0[(((size_t)zg * n + c) * qpq + QPAD + r) * FQ_CG + cc] =
+          make_float4(T(cc * ZC, rr, cl), T(cc * ZC + 1, rr, cl), T(cc * ZC + 2, rr, cl), T(cc * ZC + 3, rr, cl));
   }
 }
 
@@ -714,8 +714,8 @@ static int launch_sino_to_int(const tmb_geom *g, const float *sino, float4 *sint
 
 static int launch_vol_to_int(const tmb_geom *g, const float *vol, float4 *v0, float4 *v1, cudaStream_t st) {
   if (g->fp_q) {
-    dim3 gridq((g->d.n + 31) / 32, (g->d.n + 31) / 32, g->d.nzg * FQ_CG / 2);
-    k_vol_to_intq<<<gridq, dim3(32, 8), 0, st>>>(vol, v0, v1, g->d.nz, g->d.n, g->d.qpq);
+    dim3 gridq((g->d.n + 31) / 32, (g->d.n + 7) / 8, g->d.nzg);
+    k_vol_to_intq<<<gridq, 256, 0, st>>>(vol, v0, v1, g->d.nz, g->d.n, g->d.qpq);
     return check_launch("k_vol_to_intq");
   }
   dim3 grid((g->d.n + 31) / 32, (g->d.n + 31) / 32, g->d.nzc);
