@@ -53,3 +53,20 @@ def rel_max(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def single_iteration_tv():
+    """Whole-volume PD_TV through the one-iteration-per-launch strip kernel: the z-sharded prox launches
+    exactly that kernel, so sharded == unsharded is a bit-for-bit statement about it (the default
+    unsharded prox pairs iterations in the fused kernel, same arithmetic, equal to ~1e-7)."""
+    from tomobar_b200._lib import lib
+
+    old = lib.tmb_tv_set_simple_kernels(3)
+    try:
+        yield
+    finally:
+        lib.tmb_tv_set_simple_kernels(old)

@@ -22,6 +22,7 @@ def _worker(rank, world, init_file, results):
         from tomobar_b200.methodsIR_CuPy import RecToolsIRCuPy
         from tomobar_b200.regularisersCuPy import PD_TV_cupy
         from tomobar_b200.regularisersCuPy import ROF_TV_cupy
+        from conftest import single_iteration_tv  # whole-volume references through the kernel the shards launch
         from tomobar_b200.zshard import ShardedPDTV, ShardedROFTV, ZShard
 
         nz, n, na = 24, 64, 48
@@ -36,7 +37,8 @@ def _worker(rank, world, init_file, results):
             # halos read over NVLink inside the kernel (two ways of ordering the iterations) / sent as messages
             for half in (False, True):
                 tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half, peer_memory=peer, sync=sync)
-                whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
+                with single_iteration_tv():
+                    whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
                 for _ in range(2):  # buffers are reused across calls
                     part = tv(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0)
                     out[f"tv_equal_half{int(half)}"] &= bool(torch.equal(sh.all_gather_volume(part), whole))
@@ -53,7 +55,9 @@ def _worker(rank, world, init_file, results):
         rec.set_zshard(sh)
         x_loc = rec.FISTA({"projection_data": sino[sh.z0:sh.z1].contiguous()}, dict(alg), dict(reg))
         x_all = sh.all_gather_volume(x_loc.contiguous())
-        ref = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, rank, 4).FISTA({"projection_data": sino}, dict(alg), dict(reg))
+        with single_iteration_tv():
+            ref = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, rank, 4).FISTA({"projection_data": sino}, dict(alg),
+                                                                          dict(reg))
         out["fista_equal"] = bool(torch.equal(x_all, ref))
         out["fista_maxdiff"] = float((x_all - ref).abs().max())
         # --- sharded ADMM-OS + ROF_TV == whole-volume run (BASELINE.json config 3 in miniature) ----------

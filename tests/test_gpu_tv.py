@@ -76,7 +76,7 @@ def test_marching_kernels_match_simple_kernels(shape, half):
 
     v = torch.from_numpy(_vol(shape, 7)).cuda()
     res = {}
-    for mode in (0, 1, 2, 3, 4):
+    for mode in (0, 1, 2, 3, 4, 5):
         old = lib.tmb_tv_set_simple_kernels(mode)
         try:
             res[mode] = (PD_TV_cupy(v, 5e-4, 9, 0, 1, 12.0, 0, half).cpu().numpy(),
@@ -85,6 +85,29 @@ def test_marching_kernels_match_simple_kernels(shape, half):
         finally:
             lib.tmb_tv_set_simple_kernels(old)
     tol = 2e-3 if half else 2e-6
-    for mode in (0, 2, 3, 4):
+    for mode in (0, 2, 3, 4, 5):
         for a, b in zip(res[mode], res[1]):
             assert rel_max(a, b) < tol
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 4), (5, 9, 124), (7, 18, 132), (9, 21, 244), (6, 16, 120), (66, 37, 364),
+                                   (40, 130, 8), (3, 2, 12)])
+@pytest.mark.parametrize("methodTV,nonneg", [(0, 0), (0, 1), (1, 1)])
+def test_fused_pairs_of_pd_iterations(shape, methodTV, nonneg):
+    """k_pd_tv3d_f2 (mode 5: two iterations per pass, nothing stored in between) against single
+    iterations of the strip kernel (mode 3) and of the one-thread-per-voxel kernel (mode 1), for even
+    and odd iteration counts; window / strip / z-run edges at every shape."""
+    from tomobar_b200._lib import lib
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy
+
+    v = torch.from_numpy(_vol(shape, 11)).cuda()
+    res = {}
+    for mode in (1, 3, 5):
+        old = lib.tmb_tv_set_simple_kernels(mode)
+        try:
+            res[mode] = [PD_TV_cupy(v, 5e-4, its, methodTV, nonneg, 12.0, 0, False).cpu().numpy() for its in (2, 7, 12)]
+        finally:
+            lib.tmb_tv_set_simple_kernels(old)
+    for a, b, c in zip(res[5], res[3], res[1]):
+        assert np.isfinite(a).all()
+        assert rel_max(a, b) < 2e-6 and rel_max(a, c) < 2e-6

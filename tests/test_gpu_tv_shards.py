@@ -7,6 +7,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import rel_max, single_iteration_tv
+
 pytestmark = pytest.mark.gpu
 
 
@@ -58,10 +60,14 @@ def test_sharded_pd_tv_is_bit_identical(shape, cuts, methodTV, nonneg, half):
     from tomobar_b200.regularisersCuPy import PD_TV_cupy
 
     v = _vol(shape, 11)
-    whole = PD_TV_cupy(v, 4e-4, 7, methodTV, nonneg, 12.0, 0, half)
+    with single_iteration_tv():
+        whole = PD_TV_cupy(v, 4e-4, 7, methodTV, nonneg, 12.0, 0, half)
     parts = _sharded_prox(v, list(cuts), 4e-4, 7, methodTV, nonneg, 12.0, half)
     torch.cuda.synchronize()
     assert torch.equal(whole, parts)
+    # the default whole-volume prox (pairs of iterations fused) agrees to rounding
+    fused = PD_TV_cupy(v, 4e-4, 7, methodTV, nonneg, 12.0, 0, half)
+    assert rel_max(fused.cpu().numpy(), whole.cpu().numpy()) < 2e-6
     # and independent blocks (the reference under HTTomo's z-chunking) do differ at the seams
     blocks = torch.cat([PD_TV_cupy(v[a:b].contiguous(), 4e-4, 7, methodTV, nonneg, 12.0, 0, half)
                         for a, b in zip([0] + list(cuts), list(cuts) + [shape[0]])], dim=0)
@@ -152,7 +158,8 @@ def test_explicit_ghost_pointers(half):
                                  1, 0, ptr(U[a][0][n0 - 1]), *[ptr(P[a][0][c][n0 - 1]) for c in range(3)], None,
                                  stream_ptr(v)), "tmb_pd_tv_iter")
     got = torch.cat([U[iters % 2][0], U[iters % 2][1]], dim=0)
-    assert torch.equal(got, PD_TV_cupy(v, 4e-4, iters, 0, 1, 12.0, 0, half))
+    with single_iteration_tv():
+        assert torch.equal(got, PD_TV_cupy(v, 4e-4, iters, 0, 1, 12.0, 0, half))
 
     R = [[torch.zeros((b - a, ny, nx), device="cuda") for (a, b) in bounds] for _ in range(2)]
     for i in range(2):
