@@ -111,3 +111,24 @@ def test_fused_pairs_of_pd_iterations(shape, methodTV, nonneg):
     for a, b, c in zip(res[5], res[3], res[1]):
         assert np.isfinite(a).all()
         assert rel_max(a, b) < 2e-6 and rel_max(a, c) < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(9, 21, 244), (66, 37, 364), (130, 64, 128), (5, 9, 124), (40, 130, 8)])
+def test_split_variant_of_the_fused_kernel(shape):
+    """k_pd_tv3d_f2s (mode 6, opt-in: the same two-iteration kernel with its warm-up / march / tail steps
+    specialised at compile time, 7 % faster at the headline size) on the shapes it was first run on."""
+    from tomobar_b200._lib import lib
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy
+
+    v = torch.from_numpy(_vol(shape, 13)).cuda()
+    res = {}
+    for mode in (3, 6):
+        old = lib.tmb_tv_set_simple_kernels(mode)
+        try:
+            res[mode] = [PD_TV_cupy(v, 5e-4, its, m, nn, 12.0, 0, False).cpu().numpy()
+                         for its, nn, m in ((2, 1, 0), (7, 0, 0), (4, 1, 1))]
+        finally:
+            lib.tmb_tv_set_simple_kernels(old)
+    for a, b in zip(res[6], res[3]):
+        assert np.isfinite(a).all() and rel_max(a, b) < 2e-6
+

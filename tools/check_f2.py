@@ -1,5 +1,6 @@
-"""Fused two-iteration PD_TV kernel (mode 5) against the strip kernel (mode 3): agreement on a few
-shapes, then ms / iteration at the given size.   usage: python tools/check_f2.py [nz n]"""
+"""Fused two-iteration PD_TV kernels (mode 5, and its compile-time-split variant, mode 6) against the
+strip kernel (mode 3): agreement on a few shapes, then ms / iteration at the given sizes.
+usage: python tools/check_f2.py [nz n [nz n ...]]"""
 import sys
 
 import torch
@@ -19,32 +20,38 @@ def run(mode, v, its, out=None, nonneg=1, method=0):
 
 def main():
     torch.manual_seed(0)
-    for shape in ((9, 21, 244), (66, 37, 364), (130, 64, 128)):
+    for shape in ((9, 21, 244), (66, 37, 364), (130, 64, 128), (5, 9, 124), (40, 130, 8)):
         v = torch.randn(*shape, device="cuda") * 0.05
-        for its in (2, 7):
-            a, b = run(5, v, its), run(3, v, its)
-            d = (a - b).abs().max().item() / b.abs().max().item()
-            print(f"shape={shape} its={its}: rel max diff {d:.3e} bit-equal={torch.equal(a, b)} finite={bool(torch.isfinite(a).all())}",
-                  flush=True)
-    nz, n = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) >= 3 else (512, 2048)
-    v = torch.randn(nz, n, n, device="cuda") * 0.02
-    out = torch.empty_like(v)
+        for its, nonneg, method in ((2, 1, 0), (7, 0, 0), (4, 1, 1)):
+            b = run(3, v, its, None, nonneg, method)
+            for mode in (5, 6):
+                a = run(mode, v, its, None, nonneg, method)
+                d = (a - b).abs().max().item() / b.abs().max().item()
+                print(f"mode {mode} shape={shape} its={its} nonneg={nonneg} methodTV={method}: rel max diff {d:.3e} "
+                      f"bit-equal={torch.equal(a, b)} finite={bool(torch.isfinite(a).all())}", flush=True)
+    args = [int(a) for a in sys.argv[1:]]
+    sizes = list(zip(args[0::2], args[1::2])) or [(512, 2048)]
     its = 20
-    for mode, name in ((3, "strip-reg"), (5, "fused-2")):
-        run(mode, v, its, out)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(3):
+    for nz, n in sizes:
+        v = torch.randn(nz, n, n, device="cuda") * 0.02
+        out = torch.empty_like(v)
+        ref = None
+        for mode, name in ((3, "strip-reg"), (5, "fused-2"), (6, "fused-2s")):
             run(mode, v, its, out)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / 3 / its
-        print(f"PD_TV {name:9s} {nz}x{n}x{n}: {ms:8.3f} ms/iter  {36 * v.numel() / ms / 1e6:8.1f} GB/s (36 B/voxel/iter)",
-              flush=True)
-        ref = out.clone() if mode == 3 else ref
-    print("headline-size agreement: rel max diff", ((out - ref).abs().max() / ref.abs().max()).item(),
-          "bit-equal", torch.equal(out, ref))
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                run(mode, v, its, out)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 3 / its
+            if ref is None:
+                ref = out.clone()
+            print(f"PD_TV {name:9s} {nz}x{n}x{n}: {ms:8.3f} ms/iter  {36 * v.numel() / ms / 1e6:8.1f} GB/s (36 B/voxel/iter)  "
+                  f"rel max diff to strips {((out - ref).abs().max() / ref.abs().max()).item():.2e}", flush=True)
+        del v, out, ref
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
