@@ -245,6 +245,9 @@ def main():
     ap.add_argument("--halo-barrier", action="store_true",
                     help="multi-GPU peer-memory halos: one all-rank barrier per TV iteration instead of "
                          "pairwise semaphores with the two neighbours")
+    ap.add_argument("--tv-pairs", action="store_true",
+                    help="multi-GPU peer-memory halos: two PD_TV iterations per pass (tmb_pd_tv_iter2), one neighbour "
+                         "synchronisation per pair (opt-in; not yet run on hardware)")
     ap.add_argument("--independent-tv", action="store_true",
                     help="multi-GPU: TV per z-shard without halo exchange (seams at the shard borders)")
     args = ap.parse_args()
@@ -253,7 +256,8 @@ def main():
                halo=("independent z-blocks" if args.independent_tv else
                      "exact, NCCL messages between inner iterations" if args.halo_messages else
                      "exact, peer loads over NVLink inside the TV kernel"
-                     + (", all-rank barrier per iteration" if args.halo_barrier else ", pairwise semaphores")))
+                     + (", all-rank barrier per iteration" if args.halo_barrier else ", pairwise semaphores")
+                     + (", two iterations per pass" if args.tv_pairs else "")))
     if args.warmup < 3:
         args.warmup = 3
 
@@ -290,6 +294,7 @@ def main():
         rec.set_zshard(shard)
         rec.tv_peer_memory = False if args.halo_messages else None
         rec.tv_sync = "barrier" if args.halo_barrier else "signals"
+        rec.tv_pairs = True if args.tv_pairs else None
     rec.nonneg_regul = 1
     A = rec.Atools
     # synthetic data generated on the device, slice blocks of 16 to bound temporaries
@@ -360,7 +365,8 @@ def main():
     fp_launches = max(1, lib.tmb_geom_fp_launches(A._g, 0))
     # PD_TV: the unsharded prox (tmb_pd_tv) does pairs of iterations per launch where the fused kernel
     # applies; the z-sharded prox (tmb_pd_tv_iter) launches every iteration
-    tv_launches = (30 if admm else (cfg["tv_iters"] if world > 1 else
+    pairs_sharded = world > 1 and args.tv_pairs and not args.halo_messages and not args.half
+    tv_launches = (30 if admm else ((cfg["tv_iters"] + 1) // 2 if pairs_sharded else cfg["tv_iters"] if world > 1 else
                                     lib.tmb_pd_tv_launches(nz_loc, n, n, cfg["tv_iters"], int(bool(args.half)))))
     launches_per_step = 1 + fp_launches + 1 + 1 + tv_launches + 1
 
@@ -422,7 +428,7 @@ def main():
     fused_tv = (not admm) and tv_rep_launches < tv_reps
     ms_tv_launch = ms_tv * tv_reps / tv_rep_launches
     tv_gbs = bytes_tv / (ms_tv_launch * 1e-3) / 1e9
-    if world > 1 and fused_tv:
+    if world > 1 and fused_tv and not pairs_sharded:
         # the sharded step launches single iterations (strip kernel): time that kernel for the roofline
         old_mode = lib.tmb_tv_set_simple_kernels(3)
         try:

@@ -133,6 +133,22 @@ int tmb_pd_tv_iter(const float *in, const float *u_in, float *u_out, const void 
                    int half_precision, int ghost_lo, int ghost_hi, const float *u_lo, const void *p1_lo,
                    const void *p2_lo, const void *p3_lo, const float *u_hi, void *stream);
 
+/* TWO Chambolle-Pock iterations (two trips of the loop of regularisersCuPy.py:255-292) in one pass over
+ * the same caller-owned buffers, fp32 duals: the intermediate iterate is never written out, so a pair
+ * of iterations costs 36 B/voxel of HBM traffic instead of 72, and a z-shard needs its ghost planes
+ * refreshed / its neighbours synchronised once per PAIR.  The pass reaches two planes deep: with
+ * ghost_lo planes -2 and -1 of u_in and p1_in..p3_in and plane -1 of `in` must exist, with ghost_hi
+ * planes dz and dz+1 of u_in and plane dz of p1_in..p3_in and `in`.  u_lo / p*_lo point at plane -2,
+ * in_lo at plane -1, u_hi / p*_hi / in_hi at plane dz (NULL = adjacent memory; peer pointers allowed
+ * as for tmb_pd_tv_iter).  Needs dx % 4 == 0, 16-byte aligned arrays and shards of >= 2 planes
+ * (TMB_ERR_UNSUPPORTED otherwise).  Same arithmetic as two tmb_pd_tv_iter calls.                  */
+int tmb_pd_tv_iter2(const float *in, const float *u_in, float *u_out, const float *p1_in, const float *p2_in,
+                    const float *p3_in, float *p1_out, float *p2_out, float *p3_out, int dz, int dy, int dx,
+                    float regularisation_parameter, int methodTV, int nonneg, float lipschitz_const,
+                    int ghost_lo, int ghost_hi, const float *u_lo, const float *p1_lo, const float *p2_lo,
+                    const float *p3_lo, const float *in_lo, const float *u_hi, const float *p1_hi,
+                    const float *p2_hi, const float *p3_hi, const float *in_hi, void *stream);
+
 /* One ROF iteration on caller-owned ping-pong buffers (rudin_osher_fatemi_total_variation.cu:157-248,
  * both kernels fused; regularisersCuPy.py:112-162 launches them per iteration).  z-SHARDS: with
  * ghost_hi plane dz of u_in must exist; with ghost_lo planes -2 and -1 must exist (the normalised z

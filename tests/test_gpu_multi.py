@@ -42,6 +42,15 @@ def _worker(rank, world, init_file, results):
                 for _ in range(2):  # buffers are reused across calls
                     part = tv(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0)
                     out[f"tv_equal_half{int(half)}"] &= bool(torch.equal(sh.all_gather_volume(part), whole))
+            if peer and os.environ.get("TMB_TEST_UNVALIDATED"):
+                # pairs of iterations per pass over peer memory (not yet run on hardware, see ShardedPDTV)
+                tvp = ShardedPDTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=True, sync=sync, pairs=True)
+                with single_iteration_tv():
+                    whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, False)
+                for _ in range(2):
+                    part = sh.all_gather_volume(tvp(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0))
+                    out["tv_pairs_maxdiff"] = max(out.get("tv_pairs_maxdiff", 0.0),
+                                                  float((part - whole).abs().max() / whole.abs().max()))
             rof = ShardedROFTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=peer, sync=sync)
             part = rof(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 1e-3)
             out["rof_equal"] &= bool(torch.equal(sh.all_gather_volume(part),
@@ -90,5 +99,6 @@ def test_multi_gpu_sharded_tv_and_fista(world):
         assert res["rof_equal"], res
         assert res["fista_equal"], res
         assert res["admm_equal"], res
+        assert res.get("tv_pairs_maxdiff", 0.0) < 2e-6, res
         assert res["L_sharded"] == pytest.approx(res["L_whole"], rel=1e-3)
     assert all(results[r]["L_sharded"] == results[0]["L_sharded"] for r in range(world))

@@ -3,6 +3,8 @@ through ``tmb_pd_tv_iter`` with their ghost planes refreshed by plain copies bet
 iterations (what ``ShardedPDTV`` does with point-to-point messages).  The assembled result must be
 bit-identical to the whole-volume prox.  (The multi-process version: tests/test_gpu_multi.py.)"""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -172,3 +174,76 @@ def test_explicit_ghost_pointers(half):
                                   ptr(R[a][0][cut - 2]), None, stream_ptr(v)), "tmb_rof_tv_iter")
     got = torch.cat([R[iters % 2][0], R[iters % 2][1]], dim=0)
     assert torch.equal(got, ROF_TV_cupy(v, 4e-4, iters, 1e-3, 0, half))
+
+
+# ---- pairs of iterations per pass (tmb_pd_tv_iter2) -------------------------------------------------
+def _sharded_prox_pairs(v, cuts, lam, iters, methodTV, nonneg, lip):
+    """z-blocks advanced in lock step, two iterations per pass: U keeps two ghost planes on either side,
+    P two below and one above, Input one on either side (adjacent memory, refreshed by copies once per
+    PAIR); an odd last iteration goes through tmb_pd_tv_iter on the same buffers."""
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr, stream_ptr
+
+    nz, ny, nx = v.shape
+    bounds = list(zip([0] + cuts, cuts + [nz]))
+    S = []
+    for (z0, z1) in bounds:
+        nzl = z1 - z0
+        U = [torch.zeros((nzl + 4, ny, nx), device="cuda") for _ in range(2)]
+        P = [[torch.zeros((nzl + 3, ny, nx), device="cuda") for _ in range(3)] for _ in range(2)]
+        D = torch.zeros((nzl + 2, ny, nx), device="cuda")
+        U[0][2:nzl + 2] = v[z0:z1]
+        D[1:nzl + 1] = v[z0:z1]
+        S.append(dict(nzl=nzl, U=U, P=P, D=D))
+    for i, s in enumerate(S):  # Input halos never change
+        if i + 1 < len(S):
+            S[i + 1]["D"][0].copy_(s["D"][s["nzl"]])
+            s["D"][s["nzl"] + 1].copy_(S[i + 1]["D"][1])
+
+    def refresh(a):
+        for i, s in enumerate(S):
+            if i + 1 < len(S):
+                nxt, n = S[i + 1], s["nzl"]
+                nxt["U"][a][0:2].copy_(s["U"][a][n:n + 2])          # its planes -2, -1 = our last two
+                s["U"][a][n + 2:n + 4].copy_(nxt["U"][a][2:4])       # our planes dz, dz+1 = its first two
+                for c in range(3):
+                    nxt["P"][a][c][0:2].copy_(s["P"][a][c][n:n + 2])
+                    s["P"][a][c][n + 2].copy_(nxt["P"][a][c][2])
+
+    it, a = 0, 0
+    while it < iters:
+        b = 1 - a
+        refresh(a)
+        pair = it + 2 <= iters
+        for i, s in enumerate(S):
+            U, P, D, nzl = s["U"], s["P"], s["D"], s["nzl"]
+            lo, hi = int(i > 0), int(i + 1 < len(S))
+            if pair:
+                check(lib.tmb_pd_tv_iter2(ptr(D[1:]), ptr(U[a][2:]), ptr(U[b][2:]), *[ptr(P[a][c][2:]) for c in range(3)],
+                                          *[ptr(P[b][c][2:]) for c in range(3)], nzl, ny, nx, lam, methodTV, nonneg,
+                                          lip, lo, hi, *([None] * 10), stream_ptr(v)), "tmb_pd_tv_iter2")
+            else:
+                check(lib.tmb_pd_tv_iter(ptr(D[1:]), ptr(U[a][2:]), ptr(U[b][2:]), *[ptr(P[a][c][2:]) for c in range(3)],
+                                         *[ptr(P[b][c][2:]) for c in range(3)], nzl, ny, nx, lam, methodTV, nonneg,
+                                         lip, 0, lo, hi, None, None, None, None, None, stream_ptr(v)), "tmb_pd_tv_iter")
+        it += 2 if pair else 1
+        a = b
+    return torch.cat([s["U"][a][2:s["nzl"] + 2] for s in S], dim=0)
+
+
+@pytest.mark.skipif(not os.environ.get("TMB_TEST_UNVALIDATED"),
+                    reason="tmb_pd_tv_iter2 (fused pairs of PD_TV iterations on z-shards) was written after the "
+                           "round's GPU budget ended: its index logic is verified by the CPU emulation "
+                           "(tests/test_pd_fused2_emulation.py), its first GPU run is round 2's first item")
+@pytest.mark.parametrize("shape,cuts", [((40, 36, 64), [20]), ((45, 21, 132), [8, 30]), ((70, 16, 260), [2, 36]),
+                                        ((96, 8, 128), [48])])
+@pytest.mark.parametrize("methodTV,nonneg,iters", [(0, 1, 6), (1, 0, 7)])
+def test_sharded_pairs_of_pd_iterations(shape, cuts, methodTV, nonneg, iters):
+    from tomobar_b200.regularisersCuPy import PD_TV_cupy
+
+    v = _vol(shape, 17)
+    with single_iteration_tv():
+        whole = PD_TV_cupy(v, 4e-4, iters, methodTV, nonneg, 12.0, 0, False)
+    parts = _sharded_prox_pairs(v, list(cuts), 4e-4, iters, methodTV, nonneg, 12.0)
+    torch.cuda.synchronize()
+    assert rel_max(parts.cpu().numpy(), whole.cpu().numpy()) < 2e-6

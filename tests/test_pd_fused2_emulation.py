@@ -29,3 +29,15 @@ def emu():
 ])
 def test_emulated_kernel_equals_two_plain_iterations(emu, shape, zrun, nonneg, aniso):
     assert emu.run_case(shape, zrun, nonneg, aniso, seed=sum(shape))
+
+
+@pytest.mark.parametrize("shape,cuts,zrun,nonneg,aniso", [
+    ((8, 9, 124), [4], 4, True, False),
+    ((9, 6, 12), [2, 5], 2, False, False),      # shards of 2, 3 and 4 planes
+    ((10, 18, 132), [3, 7], 8, False, True),
+    ((6, 5, 8), [2, 4], 1, True, False),        # every z-run starts in the neighbour's planes
+])
+def test_emulated_sharded_kernel_equals_two_plain_iterations(emu, shape, cuts, zrun, nonneg, aniso):
+    """The GHOST variant (tmb_pd_tv_iter2): every z-shard emulated on its own, reading two ghost planes
+    of U and one of P / Input from its neighbours' arrays; assembled result == whole volume, bit for bit."""
+    assert emu.run_sharded_case(shape, cuts, zrun, nonneg, aniso, seed=sum(shape) + len(cuts))

@@ -43,6 +43,7 @@ SIGNATURES = {
     "tmb_rof_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _f, _i, _vp, _vp]),
     "tmb_pd_tv_iter": (_i, [_fp, _fp, _fp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _f, _i, _i, _i,
                             _fp, _vp, _vp, _vp, _fp, _vp]),
+    "tmb_pd_tv_iter2": (_i, [_fp] * 9 + [_i, _i, _i, _f, _i, _i, _f, _i, _i] + [_fp] * 10 + [_vp]),
     "tmb_rof_tv_iter": (_i, [_fp, _fp, _fp, _i, _i, _i, _f, _f, _i, _i, _i, _fp, _fp, _vp]),
     "tmb_tv_set_simple_kernels": (_i, [_i]),
     "tmb_pd_tv_launches": (_i, [_i, _i, _i, _i, _i]),

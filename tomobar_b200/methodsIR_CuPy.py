@@ -87,6 +87,7 @@ class RecToolsIRCuPy:
         self.zshard = None   # set_zshard(): this object reconstructs one z-block of a larger volume
         self.tv_peer_memory = None  # sharded TV halos: None = NVLink peer loads on NCCL, False = messages
         self.tv_sync = "signals"    # peer-memory ordering: pairwise semaphores, or "barrier"
+        self.tv_pairs = None        # sharded PD_TV: two iterations per pass (None: TMB_SHARDED_PAIRS, off by default)
         self._sharded_tv = {}
 
     def set_zshard(self, shard) -> None:
@@ -289,7 +290,8 @@ class RecToolsIRCuPy:
 
                 key = ("pd", tuple(X.shape), bool(reg.get("half_precision", False)))
                 if key not in self._sharded_tv:
-                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2], self.tv_peer_memory, self.tv_sync)}
+                    self._sharded_tv = {key: ShardedPDTV(sh, key[1], X.device, key[2], self.tv_peer_memory, self.tv_sync,
+                                                          self.tv_pairs)}
                 return self._sharded_tv[key](X, reg["regul_param"], reg["iterations"], reg["methodTV"],
                                              self.nonneg_regul, reg["PD_LipschitzConstant"], out=out)
             return PD_TV_cupy(X, reg["regul_param"], reg["iterations"], reg["methodTV"], self.nonneg_regul,

@@ -22,6 +22,7 @@ Nothing here touches the CUDA library except the two ``Sharded*TV`` classes; the
 
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -203,15 +204,27 @@ class ShardedPDTV:
     * ``peer_memory=False``: ghost planes next to the shard, refreshed with point-to-point messages
       (5 planes per rank per iteration) before each launch.
 
+    ``pairs=True`` (peer memory, fp32 duals; opt-in, also ``TMB_SHARDED_PAIRS=1``): two iterations per
+    pass through ``tmb_pd_tv_iter2`` -- the kernel reaches two planes into each neighbour (U, P1..P3
+    and the prox input, which then lives in symmetric memory too) and the neighbours synchronise once
+    per PAIR of iterations.  NOT yet run on hardware (written after round 1's GPU budget ended; the
+    kernel's index logic is covered by tests/test_pd_fused2_emulation.py): hence off by default.
+
     Buffers are allocated once and reused across calls."""
 
     def __init__(self, shard: ZShard, shape: Tuple[int, int, int], device: torch.device, half_precision: bool = False,
-                 peer_memory: Optional[bool] = None, sync: str = "signals"):
+                 peer_memory: Optional[bool] = None, sync: str = "signals", pairs: Optional[bool] = None):
         nzl, ny, nx = shape
         if nzl != shard.nz_local:
             raise ValueError("ShardedPDTV: the volume shard does not match the z-partition")
         self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
         self.peer = _peer_memory_default(shard, device) if peer_memory is None else bool(peer_memory)
+        if pairs is None:
+            pairs = os.environ.get("TMB_SHARDED_PAIRS", "0") == "1"
+        # pairs of iterations: peer memory, fp32 duals, rows of whole float4s, every shard >= 2 planes
+        self.pairs = bool(pairs) and self.peer and not self.half and nx % 4 == 0 and ny >= 2 and \
+            min(shard_bounds(shard.nz_total, shard.world, r, shard.multiple)[1] -
+                shard_bounds(shard.nz_total, shard.world, r, shard.multiple)[0] for r in range(shard.world)) >= 2
         pdt = torch.float16 if self.half else torch.float32
         # U: ghost plane below (index 0) and above (index nzl + 1); P: ghost plane below only
         if not self.peer:
@@ -223,13 +236,15 @@ class ShardedPDTV:
         esz = 2 if self.half else 4
         self._ub, self._pb = (per + 2) * plane * 4, (per + 1) * plane * esz
         self._plane, self._esz = plane, esz
-        self.slab = _PeerSlab(2 * self._ub + 6 * self._pb, device, shard.group)
+        self._db = 2 * self._ub + 6 * self._pb  # offset of the prox input (pairs only)
+        self.slab = _PeerSlab(self._db + (per * plane * 4 if self.pairs else 0), device, shard.group)
         self.slab.buf.zero_()
         self.slab.barrier()
         self.sync = _NeighbourSync(self.slab, shard, sync)
         self.U = [self.slab.view(a * self._ub, (nzl + 2, ny, nx), torch.float32) for a in range(2)]
         self.P = [[self.slab.view(2 * self._ub + (a * 3 + c) * self._pb, (nzl + 1, ny, nx), pdt) for c in range(3)]
                   for a in range(2)]
+        self.D = self.slab.view(self._db, (nzl, ny, nx), torch.float32) if self.pairs else None
 
     def _ghost_ptrs(self, a: int):
         """Peer addresses of the halo planes of ping-pong set ``a``."""
@@ -244,6 +259,27 @@ class ShardedPDTV:
         if sh.next is not None:
             u_hi = self.slab.ptrs[sh._global(sh.next)] + a * self._ub + plane * 4  # its first own plane
         return u_lo, p_lo, u_hi
+
+    def _ghost_ptrs2(self, a: int):
+        """Peer addresses a fused pass needs from ping-pong set ``a``: the neighbours' last / first TWO
+        planes of U, two / one planes of P1..P3 and one plane of the prox input (10 pointers in the
+        argument order of ``tmb_pd_tv_iter2``)."""
+        sh, plane = self.shard, self._plane
+        lo = [None] * 5
+        hi = [None] * 5
+        if sh.prev is not None:
+            base = self.slab.ptrs[sh._global(sh.prev)]
+            z0p, z1p = shard_bounds(sh.nz_total, sh.world, sh.prev, sh.multiple)
+            top = z1p - z0p  # its own planes sit at indices 1 .. top of U and P, 0 .. top - 1 of the input
+            lo = [base + a * self._ub + (top - 1) * plane * 4]
+            lo += [base + 2 * self._ub + (a * 3 + c) * self._pb + (top - 1) * plane * 4 for c in range(3)]
+            lo += [base + self._db + (top - 1) * plane * 4]
+        if sh.next is not None:
+            base = self.slab.ptrs[sh._global(sh.next)]
+            hi = [base + a * self._ub + plane * 4]
+            hi += [base + 2 * self._ub + (a * 3 + c) * self._pb + plane * 4 for c in range(3)]
+            hi += [base + self._db]
+        return lo + hi
 
     def __call__(self, data: torch.Tensor, regularisation_parameter: float, iterations: int, methodTV: int = 0,
                  nonneg: int = 0, lipschitz_const: float = 8.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -260,9 +296,14 @@ class ShardedPDTV:
         U[0][1:nzl + 1].copy_(data)
         for c in range(3):
             P[0][c].zero_()
+        if self.pairs:
+            self.D.copy_(data)  # the neighbours read one plane of the prox input as well
         if self.peer:
             self.sync.produced()
         ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
+        if self.pairs:
+            return self._run_pairs(data, regularisation_parameter, int(iterations), methodTV, nonneg, lipschitz_const,
+                                   ghost_lo, ghost_hi, out)
         with torch.cuda.device(self.device):
             for it in range(int(iterations)):
                 a, b = it % 2, 1 - it % 2
@@ -287,6 +328,43 @@ class ShardedPDTV:
                 if self.peer:
                     self.sync.produced()
         res = U[int(iterations) % 2][1:nzl + 1]
+        if out is None:
+            return res.clone()
+        out.copy_(res)
+        return out
+
+
+    def _run_pairs(self, data, lam, iterations, methodTV, nonneg, lip, ghost_lo, ghost_hi, out):
+        """Pairs of iterations per pass (peer memory): one neighbour synchronisation per launch."""
+        from tomobar_b200._lib import lib, check
+        from tomobar_b200._tensors import ptr, stream_ptr
+
+        nzl, ny, nx = self.shape
+        U, P, D = self.U, self.P, self.D
+        it, a = 0, 0
+        with torch.cuda.device(self.device):
+            while it < iterations:
+                b = 1 - a
+                self.sync.acquire()  # the neighbours have finished writing set `a` and reading set `b`
+                if it + 2 <= iterations:
+                    g = self._ghost_ptrs2(a)
+                    check(lib.tmb_pd_tv_iter2(ptr(D), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
+                                              ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
+                                              nzl, ny, nx, float(lam), int(methodTV), int(nonneg), float(lip),
+                                              ghost_lo, ghost_hi, *g, stream_ptr(data)), "tmb_pd_tv_iter2")
+                    it += 2
+                else:
+                    u_lo, p_lo, u_hi = self._ghost_ptrs(a)
+                    p_lo = p_lo or [None, None, None]
+                    check(lib.tmb_pd_tv_iter(ptr(D), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
+                                             ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
+                                             nzl, ny, nx, float(lam), int(methodTV), int(nonneg), float(lip), 0,
+                                             ghost_lo, ghost_hi, u_lo, p_lo[0], p_lo[1], p_lo[2], u_hi,
+                                             stream_ptr(data)), "tmb_pd_tv_iter")
+                    it += 1
+                self.sync.produced()
+                a = b
+        res = U[a][1:nzl + 1]
         if out is None:
             return res.clone()
         out.copy_(res)

@@ -65,8 +65,23 @@ def iterate_plain(inp, U, P, sigma, tau, lt, theta, nonneg, aniso):
     return Un, [a.astype(F32) for a in q]
 
 
-def emulate(inp, U, P, sigma, tau, lt, theta, nonneg, aniso, zrun):
+def emulate(inp, U, P, sigma, tau, lt, theta, nonneg, aniso, zrun, below=None, above=None):
+    """below / above: (inp, U, P) of the neighbouring z-shards, or None at the ends of the volume.  With a
+    neighbour the kernel reads two ghost planes of U (one of P and Input) on that side straight from the
+    neighbour's arrays -- plane -1 is the neighbour's last plane, plane dz its first."""
     dz, dy, dx = U.shape
+    lo, hi = below is not None, above is not None
+
+    def plane(name, comp, z):
+        """Plane z of array `name` (\"in\", \"U\", \"P\") as the kernel addresses it."""
+        src = {"in": lambda t: t[0], "U": lambda t: t[1], "P": lambda t: t[2][comp]}[name]
+        if z < 0:
+            assert lo and z >= -2 and (name != "in" or z == -1)
+            return src(below)[z]           # python's negative index: -1 = last plane of the shard below
+        if z >= dz:
+            assert hi and z - dz <= (1 if name == "U" else 0)
+            return src(above)[z - dz]
+        return src((inp, U, P))[z]
     Uo = np.full_like(U, np.nan)
     Q = [np.full_like(U, np.nan) for _ in range(3)]
     stores = np.zeros(U.shape, dtype=np.int32)
@@ -93,15 +108,15 @@ def emulate(inp, U, P, sigma, tau, lt, theta, nonneg, aniso, zrun):
         rows = np.clip(y0 - 2 + np.arange(ROWS), 0, dy - 1)
         sm = np.full((32, 32, 4), np.nan, dtype=F32)  # [slot, lane, component]
 
-        def ldv4(a, z, k):
-            return a[z, rows[k]][cols].astype(F32)
+        def ldv4(name, comp, z, k):
+            return plane(name, comp, z)[rows[k]][cols].astype(F32)
 
         def load_packet(z, k):
-            pk = {"un": ldv4(U, z - 1 if z == dz - 1 else z + 1, k)}
+            pk = {"un": ldv4("U", 0, z - 1 if (z == dz - 1 and not hi) else z + 1, k)}
             if k <= S + 2:
-                pk["p1"], pk["p2"], pk["p3"] = ldv4(P[0], z, k), ldv4(P[1], z, k), ldv4(P[2], z, k)
+                pk["p1"], pk["p2"], pk["p3"] = ldv4("P", 0, z, k), ldv4("P", 1, z, k), ldv4("P", 2, z, k)
                 if k >= 1:
-                    pk["in"] = ldv4(inp, z, k)
+                    pk["in"] = ldv4("in", 0, max(z, -1), k)  # plane -2 of Input is never needed: clamped
             return pk
 
         def dual_row(p1, p2, p3, u, uy, un, lastx):
@@ -117,14 +132,18 @@ def emulate(inp, U, P, sigma, tau, lt, theta, nonneg, aniso, zrun):
             return primal(u, q1, p1m, q2, pmy, q3, pmz, inn, tau, lt, theta, nonneg)
 
         zs, zB0 = max(za - 2, 0), max(za - 1, 0)
-        uc = [ldv4(U, zs, k) for k in range(ROWS)]
+        if lo:
+            zs, zB0 = za - 2, za - 1  # planes below 0 exist: they are the neighbour's
+        zlast = zb if hi else min(zb, dz - 1)  # last plane of iteration A (plane dz is the neighbour's)
+        uc = [ldv4("U", 0, zs, k) for k in range(ROWS)]
         p3b = [np.zeros((32, 4), F32) for _ in range(S)]
         nxt = load_packet(zs, 0)
         zero4 = np.zeros((32, 4), F32)
-        for z in range(zs, zb + 1):
-            doA, doB, emit, hasz = z < dz, z - 1 >= zB0, z - 1 >= za, z > 0
-            more = z + 1 <= zb and z + 1 < dz
-            ua_dst = UA2 if z == dz - 1 else UA
+        steps = list(range(zs, zlast + 1)) + ([dz] if (zb == dz and not hi) else [])  # + the tail step
+        for z in steps:
+            doA, doB, emit, hasz = z <= zlast, z - 1 >= zB0, z - 1 >= za, (z > 0 or lo)
+            more = z + 1 <= zlast
+            ua_dst = UA2 if (z == dz - 1 and not hi) else UA
             cen_src = UA if doA else UA2
             p2a = p2b = cen_prev = un_saved = None
             for k in range(ROWS):
@@ -206,8 +225,39 @@ def run_case(shape, zrun, nonneg, aniso, seed):
     return ok
 
 
+def run_sharded_case(shape, cuts, zrun, nonneg, aniso, seed):
+    """The volume cut into z-shards, every shard emulated on its own with ghost reads from its
+    neighbours' arrays; the assembled result must equal two plain iterations of the whole volume."""
+    rng = np.random.default_rng(seed)
+    inp = rng.standard_normal(shape).astype(F32)
+    U = (inp + 0.3 * rng.standard_normal(shape)).astype(F32)
+    P = [(0.7 * rng.standard_normal(shape)).astype(F32) for _ in range(3)]
+    sigma, tau, lt, theta = F32(0.9), F32(0.05), F32(0.37), F32(1.0)
+    U1, P1 = iterate_plain(inp, U, P, sigma, tau, lt, theta, nonneg, aniso)
+    U2, P2 = iterate_plain(inp, U1, P1, sigma, tau, lt, theta, nonneg, aniso)
+    bounds = list(zip([0] + list(cuts), list(cuts) + [shape[0]]))
+    shards = [(inp[a:b], U[a:b], [c[a:b] for c in P]) for a, b in bounds]
+    outs, ok = [], True
+    for i, sh in enumerate(shards):
+        Uo, Q, stores = emulate(sh[0], sh[1], sh[2], sigma, tau, lt, theta, nonneg, aniso, zrun,
+                                below=shards[i - 1] if i > 0 else None,
+                                above=shards[i + 1] if i + 1 < len(shards) else None)
+        ok = ok and np.array_equal(stores, np.ones_like(stores))
+        outs.append((Uo, Q))
+    Ug = np.concatenate([o[0] for o in outs], axis=0)
+    Qg = [np.concatenate([o[1][c] for o in outs], axis=0) for c in range(3)]
+    ok = ok and np.array_equal(Ug, U2) and all(np.array_equal(Qg[c], P2[c]) for c in range(3))
+    print(f"sharded shape={shape} cuts={cuts} zrun={zrun} nonneg={nonneg} aniso={aniso}: {'OK' if ok else 'MISMATCH'} "
+          f"(bad U {np.count_nonzero(Ug != U2)}, bad P {[int(np.count_nonzero(Qg[c] != P2[c])) for c in range(3)]})")
+    return ok
+
+
 def main():
     ok = True
+    ok &= run_sharded_case((8, 9, 124), [4], 4, True, False, 10)
+    ok &= run_sharded_case((9, 6, 12), [2, 5], 2, False, False, 11)
+    ok &= run_sharded_case((10, 18, 132), [3, 7], 8, False, True, 12)
+    ok &= run_sharded_case((6, 5, 8), [2, 4], 1, True, False, 13)
     ok &= run_case((2, 3, 8), 2, False, False, 0)
     ok &= run_case((5, 9, 124), 5, True, False, 1)
     ok &= run_case((7, 18, 132), 3, False, False, 2)
