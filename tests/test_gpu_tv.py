@@ -136,22 +136,24 @@ def test_split_variant_of_the_fused_kernel(shape):
 
 
 @pytest.mark.skipif(not os.environ.get("TMB_TEST_UNVALIDATED"),
-                    reason="hook 7 (split fused kernel at four CTAs per SM) was written after the round's GPU "
-                           "budget ended; its first GPU run is part of round 2")
+                    reason="hooks 7 / 8 (split fused kernel at four CTAs per SM / with packets two rows ahead) were "
+                           "written after the round's GPU budget ended (their source runs on the CPU warp shim); "
+                           "first GPU run in round 2")
+@pytest.mark.parametrize("mode", [7, 8])
 @pytest.mark.parametrize("shape", [(9, 21, 244), (66, 37, 364), (2, 2, 4), (7, 18, 132)])
-def test_four_ctas_per_sm_variant_of_the_fused_kernel(shape):
+def test_untimed_variants_of_the_fused_kernel(shape, mode):
     from tomobar_b200._lib import lib
     from tomobar_b200.regularisersCuPy import PD_TV_cupy
 
     v = torch.from_numpy(_vol(shape, 13)).cuda()
     res = {}
-    for mode in (3, 7):
-        old = lib.tmb_tv_set_simple_kernels(mode)
+    for hook in (3, mode):
+        old = lib.tmb_tv_set_simple_kernels(hook)
         try:
-            res[mode] = [PD_TV_cupy(v, 5e-4, its, m, nn, 12.0, 0, False).cpu().numpy()
+            res[hook] = [PD_TV_cupy(v, 5e-4, its, m, nn, 12.0, 0, False).cpu().numpy()
                          for its, nn, m in ((2, 1, 0), (7, 0, 0), (4, 1, 1))]
         finally:
             lib.tmb_tv_set_simple_kernels(old)
-    for a, b in zip(res[7], res[3]):
+    for a, b in zip(res[mode], res[3]):
         assert np.isfinite(a).all() and rel_max(a, b) < 2e-6
 
