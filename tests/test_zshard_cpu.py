@@ -111,3 +111,43 @@ def test_two_rank_gloo_collectives_and_power_method():
         x = x / np.float32(s)
     assert results[0]["L"] == pytest.approx(s, rel=1e-5)
     assert results[0]["L"] == results[1]["L"]
+
+
+def test_peer_pointers_of_a_fused_pass():
+    """ShardedPDTV._ghost_ptrs2: where a two-iterations-per-pass launch looks for its ghost planes inside the
+    neighbours' symmetric-memory slabs (host arithmetic only: the slab layout is U[2] | P[2][3] | input)."""
+    from types import SimpleNamespace
+
+    from tomobar_b200.zshard import ShardedPDTV
+
+    nz_total, world, ny, nx = 22, 3, 6, 8          # shards of 8, 8 and 6 planes
+    plane = ny * nx
+    per = shard_bounds(nz_total, world, 0, 2)[1]
+    ub, pb = (per + 2) * plane * 4, (per + 1) * plane * 4
+    bases = [1 << 40, 2 << 40, 3 << 40]
+
+    def make(rank):
+        tv = object.__new__(ShardedPDTV)
+        tv.shard = SimpleNamespace(nz_total=nz_total, world=world, multiple=2, rank=rank,
+                                   prev=rank - 1 if rank > 0 else None, next=rank + 1 if rank + 1 < world else None,
+                                   _global=lambda peer: peer)
+        tv._plane, tv._esz, tv._ub, tv._pb, tv._db = plane, 4, ub, pb, 2 * ub + 6 * pb
+        tv.slab = SimpleNamespace(ptrs=bases)
+        return tv
+
+    for a in (0, 1):
+        g = make(1)._ghost_ptrs2(a)                # the middle shard has both neighbours
+        lo_n = 8                                   # planes of shard 0: its own planes are U[1..8], P[1..8], input[0..7]
+        assert g[0] == bases[0] + a * ub + (lo_n - 1) * plane * 4                              # U planes -2, -1
+        assert g[1:4] == [bases[0] + 2 * ub + (a * 3 + c) * pb + (lo_n - 1) * plane * 4 for c in range(3)]
+        assert g[4] == bases[0] + 2 * ub + 6 * pb + (lo_n - 1) * plane * 4                      # input plane -1
+        assert g[5] == bases[2] + a * ub + plane * 4                                           # U planes dz, dz+1
+        assert g[6:9] == [bases[2] + 2 * ub + (a * 3 + c) * pb + plane * 4 for c in range(3)]
+        assert g[9] == bases[2] + 2 * ub + 6 * pb                                              # input plane dz
+        first, last = make(0)._ghost_ptrs2(a), make(2)._ghost_ptrs2(a)
+        assert first[:5] == [None] * 5 and all(p is not None for p in first[5:])
+        assert last[5:] == [None] * 5 and all(p is not None for p in last[:5])
+        # U_lo must address the same bytes as the single-iteration ghost pointer, one plane earlier
+        u_lo1, p_lo1, u_hi1 = make(1)._ghost_ptrs(a)
+        assert g[0] == u_lo1 - plane * 4 and g[5] == u_hi1
+        assert g[1:4] == [p - plane * 4 for p in p_lo1]
