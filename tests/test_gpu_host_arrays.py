@@ -64,3 +64,26 @@ def test_errors(scan):
         RecToolsDIR(160, 0, None, 0.0, angles, 160)
     with pytest.raises(ValueError):
         _rec(data, angles).FBP(data.astype(np.float64), data_axes_labels_order=LABELS)
+
+
+def test_fourier_inv_estimate_against_the_allocator():
+    """The dry-run estimate (DeviceMemStack protocol) against torch's own peak statistic."""
+    import torch
+
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+    from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+    nz, nproj, n = 64, 600, 1024
+    angles = np.linspace(0, np.pi, nproj, endpoint=False).astype(np.float32)
+    R = RecToolsDIRCuPy(n, 0, nz, 0.0, angles, n, device_projector=0)
+    with DeviceMemStack() as st:
+        assert R.FOURIER_INV((nz, nproj, n), data_dtype=np.float32) == (nz, n, n)
+    data = torch.rand((nz, nproj, n), device="cuda")
+    R.FOURIER_INV(data)  # cuFFT plans and the like are created on the first call
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    before = torch.cuda.memory_allocated()
+    R.FOURIER_INV(data)
+    torch.cuda.synchronize()
+    measured = torch.cuda.max_memory_allocated() - before + data.numel() * 4
+    assert 0.6 * st.highwater <= measured <= 1.05 * st.highwater, (measured, st.highwater)

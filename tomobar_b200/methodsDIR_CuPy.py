@@ -120,6 +120,10 @@ class RecToolsDIRCuPy:
         accepted and ignored; ``center_size`` smaller than the full grid (the scatter kernels) is
         not built.
         """
+        if isinstance(data, tuple):
+            # dry run under an active DeviceMemStack: record this implementation's allocations
+            # (the reference's estimator mode, methodsDIR_CuPy.py:253-258, 437-441)
+            return self._fourier_inv_estimator(data, **kwargs)
         kwargs.update({"cupyrun": True})
         cutoff_freq = 1.0
         filter_type = "shepp"
@@ -223,6 +227,103 @@ class RecToolsDIRCuPy:
                   "tmb_fi_unpad")
             del fde
         return check_kwargs(recon_up, **kwargs)
+
+    def _fourier_inv_estimator(self, shape, **kwargs):
+        """FOURIER_INV called with a shape tuple (after any axis swap: [detY, angles, detX]): replays the
+        allocation sequence of the method above on the active ``DeviceMemStack`` and returns the shape of
+        the reconstruction.  cuFFT work areas are counted as one copy of the transform's output (an upper
+        bound for the power-of-two sizes used here); the caller's input array is counted like the
+        reference counts it (``data_dtype`` keyword, default float32)."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
+        if stack is None:
+            raise ValueError("FOURIER_INV: a shape tuple needs an active DeviceMemStack (memory estimation)")
+        power_of_2_oversampling, power_of_2_cropping, oversampling_level, padding = True, False, 4, 0
+        for key, value in kwargs.items():
+            if value is None:
+                continue
+            if key == "data_axes_labels_order":
+                shape = _data_dims_swapper(tuple(shape), value, ["detY", "angles", "detX"])
+            elif key == "power_of_2_oversampling":
+                power_of_2_oversampling = value
+            elif key == "power_of_2_cropping":
+                power_of_2_cropping = value
+            elif key == "padding" and isinstance(value, int) and value >= 0:
+                padding = value
+        nz, nproj, data_n = (int(v) for v in shape)
+        itemsize = int(np.dtype(kwargs.get("data_dtype", np.float32)).itemsize)
+        recon_size = self.recon_size
+        if recon_size > data_n:
+            raise ValueError(
+                "The reconstruction size {} should not be larger than the size of the horizontal detector {}".format(
+                    recon_size, data_n
+                )
+            )
+        stack.malloc(nz * nproj * data_n * itemsize)  # the caller's projections stay alive throughout
+        odd_horiz, odd_vert = bool(data_n % 2), bool(nz % 2)
+        raw_nz = nz
+        data_n += odd_horiz
+        nz += odd_vert
+        padded = nz * nproj * data_n * 4 if (odd_horiz or odd_vert) else 0
+        if padded:
+            stack.malloc(padded)
+        n = data_n + self.detectors_x_pad * 2 + padding * 2
+        if power_of_2_cropping:
+            n_pow2 = 2 ** math.ceil(math.log2(n))
+            if 0.9 < n / n_pow2:
+                n = n_pow2
+        nz2 = nz // 2
+        for b in (nproj * 4, nproj * 4, nproj * 8, nproj * 4):  # theta, sorted theta, int64 / int32 indices
+            stack.malloc(b)
+        stack.free(nproj * 8)
+        # STEP 0: filter (see _fourier_filter): `out`, then per slice chunk the padded rows, their rfft, the
+        # filtered spectrum and the irfft output, plus one work area per transform
+        if power_of_2_oversampling:
+            over = 2 ** math.ceil(math.log2(data_n * 3))
+            if n > over:
+                over = 2 ** math.ceil(math.log2(n))
+        else:
+            over = max(int(oversampling_level * data_n), n)
+        tmp_p = nz * nproj * n * 4
+        stack.malloc(tmp_p)
+        per = min(nz, max(1, (1 << 27) // (nproj * over)))
+        rows_real, rows_cplx = per * nproj * over * 4, per * nproj * (over // 2 + 1) * 8
+        stack.malloc(rows_real)                       # edge-padded rows
+        stack.malloc(rows_cplx), stack.malloc(rows_cplx)   # rfft output + its work area
+        stack.free(rows_cplx)
+        stack.malloc(rows_cplx)                       # filtered spectrum
+        stack.free(rows_cplx)                         # (the rfft output is released after the product)
+        stack.malloc(rows_real), stack.malloc(rows_real)   # irfft output + its work area
+        stack.free(rows_real), stack.free(rows_cplx), stack.free(rows_real), stack.free(rows_real)
+        if padded:
+            stack.free(padded)                        # `del data`: only our padded copy goes away
+        # STEP 1: complex slice pairs and their 1-D FFT (out of place)
+        datac = nz2 * nproj * n * 8
+        stack.malloc(datac)
+        stack.free(tmp_p)
+        stack.malloc(datac), stack.malloc(datac)      # FFT output + work area
+        stack.free(datac), stack.free(datac)
+        # STEP 2: the oversampled Cartesian grid
+        fde = nz2 * (2 * n) * (2 * n) * 8
+        stack.malloc(fde)
+        stack.free(datac)
+        # STEP 3: inverse 2-D FFT in slice chunks (output chunk + work area)
+        chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))
+        piece = chunk * (2 * n) * (2 * n) * 8
+        stack.malloc(piece), stack.malloc(piece)
+        stack.free(piece), stack.free(piece)
+        # STEP 4: the reconstruction
+        odd_recon = bool(recon_size % 2)
+        um = (n - odd_horiz) // 2 - recon_size // 2
+        up = (n - odd_horiz) // 2 + (recon_size + odd_recon) // 2
+        recon_shape = (raw_nz, up - um, up - um)
+        recon = int(np.prod(recon_shape)) * 4
+        stack.malloc(recon)
+        stack.free(fde)
+        for b in (nproj * 4, nproj * 4, nproj * 4, recon):  # like the reference, the result is not kept on the stack
+            stack.free(b)
+        return recon_shape
 
     def _fourier_filter(self, data, raw_width, width, power_of_2_oversampling, oversampling_level, filter_type,
                         cutoff_freq) -> torch.Tensor:
