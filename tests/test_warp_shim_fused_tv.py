@@ -148,3 +148,24 @@ def test_z_shard_kernel_with_peer_pointers_on_the_cpu(shim, plain, shape, cuts, 
     _close(np.concatenate([o[0] for o in outs], axis=0), U2)
     for c in range(3):
         _close(np.concatenate([o[1][c] for o in outs], axis=0), P2[c])
+
+
+@pytest.mark.parametrize("shape,zrun,nonneg,aniso", [((5, 9, 124), 5, True, False), ((7, 18, 132), 3, False, True),
+                                                     ((4, 5, 4), 1, False, False)])
+def test_first_pass_variant_on_the_cpu(shim, plain, shape, zrun, nonneg, aniso):
+    """k_pd_tv3d_f2s<PZERO> (hook 6's first pass of a prox call): the dual arrays are NOT read -- they hold
+    NaN here -- and the input doubles as the primal variable; result == two plain iterations from P = 0."""
+    inp, _, _ = _case(shape, sum(shape) + 7)
+    zeros = [np.zeros(shape, F32) for _ in range(3)]
+    U2, P2 = _two_plain(plain, inp, inp, zeros, nonneg, aniso)
+    poison = [_aligned(shape, np.nan) for _ in range(3)]
+    Uo = _aligned(shape, np.nan)
+    Q = [_aligned(shape, np.nan) for _ in range(3)]
+    dz, dy, dx = shape
+    rc = shim.shim_run_fused_tv(5, int(nonneg), int(aniso), _ptr(inp), _ptr(inp), _ptr(Uo), *[_ptr(p) for p in poison],
+                                *[_ptr(q) for q in Q], SIGMA, TAU, LT, THETA, dx, dy, dz, zrun, 0, 0, *([None] * 10))
+    assert rc == 0
+    _close(Uo, U2)
+    for c in range(3):
+        _close(Q[c], P2[c])
+
