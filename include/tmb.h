@@ -162,7 +162,8 @@ int tmb_rof_tv_iter(const float *in, const float *u_in, float *u_out, int dz, in
  * the z-marching ones, 2 through the CTA-tiled z-marching kernels, 3 / 4 force the register-fed / TMA-fed
  * warp-strip PD_TV kernel (one iteration per launch), 5 the kernel that does two PD_TV iterations per
  * pass, 6 its compile-time-specialised variant, 7 that variant at four CTAs per SM, 8 with its loads two rows
- * ahead, 9 = 6 without the memset / copy at the start of a prox call (0 picks the measured best; same arithmetic, used by the parity tests).  Returns the old value. */
+ * ahead, 9 = 6 without the memset / copy at the start of a prox call, 10 = 6 with
+ * the next plane prefetched into L2 (0 picks the measured best; same arithmetic, used by the parity tests).  Returns the old value. */
 int tmb_tv_set_simple_kernels(int enable);
 /* number of kernels tmb_pd_tv launches for `iterations` iterations (PD_TV_cupy's loop,
  * regularisersCuPy.py:262-294, is one launch per iteration in the reference; here pairs of

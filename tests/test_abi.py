@@ -90,7 +90,7 @@ def test_pd_tv_launch_accounting_needs_no_gpu():
     kernel applies (fp32 duals, 3-D, rows of whole float4s), every iteration launches otherwise."""
     from tomobar_b200._lib import lib
 
-    assert lib.tmb_tv_set_simple_kernels(0) in range(0, 10)
+    assert lib.tmb_tv_set_simple_kernels(0) in range(0, 11)
     try:
         assert lib.tmb_pd_tv_launches(512, 2048, 2048, 50, 0) == 25
         assert lib.tmb_pd_tv_launches(512, 2048, 2048, 7, 0) == 4      # odd tail: one single iteration
@@ -98,7 +98,7 @@ def test_pd_tv_launch_accounting_needs_no_gpu():
         assert lib.tmb_pd_tv_launches(16, 64, 150, 10, 0) == 10         # dx % 4 != 0
         assert lib.tmb_pd_tv_launches(1, 64, 64, 10, 0) == 10           # 2-D
         assert lib.tmb_pd_tv_launches(16, 64, 64, 0, 0) == 0
-        for mode, want in ((1, 10), (2, 10), (3, 10), (4, 10), (5, 5), (6, 5), (7, 5), (8, 5), (9, 5)):
+        for mode, want in ((1, 10), (2, 10), (3, 10), (4, 10), (5, 5), (6, 5), (7, 5), (8, 5), (9, 5), (10, 5)):
             lib.tmb_tv_set_simple_kernels(mode)
             assert lib.tmb_pd_tv_launches(16, 64, 64, 10, 0) == want, mode
     finally:

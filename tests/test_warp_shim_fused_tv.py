@@ -81,7 +81,7 @@ def _close(a, b):
     assert np.max(np.abs(a - b)) <= 2e-6 * max(np.max(np.abs(b)), 1.0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6])
 @pytest.mark.parametrize("shape,zrun,nonneg,aniso", [
     ((2, 3, 8), 2, False, False),
     ((5, 9, 124), 5, True, False),
@@ -91,7 +91,7 @@ def _close(a, b):
 ])
 def test_whole_volume_kernels_on_the_cpu(shim, plain, variant, shape, zrun, nonneg, aniso):
     """0: k_pd_tv3d_f2 (the default, validated on the B200), 1: k_pd_tv3d_f2s (run on the B200 on five
-    shapes), 2: k_pd_tv3d_f2s at four CTAs per SM, 4: with packets two rows ahead (2 and 4 never ran on a GPU)."""
+    shapes), 2: k_pd_tv3d_f2s at four CTAs per SM, 4: with packets two rows ahead, 6: with L2 prefetches (2, 4 and 6 never ran on a GPU)."""
     inp, U, P = _case(shape, sum(shape))
     U2, P2 = _two_plain(plain, inp, U, P, nonneg, aniso)
     Uo = _aligned(shape, np.nan)

@@ -31,7 +31,7 @@ def main():
         v = torch.randn(nz, n, n, device="cuda") * 0.02
         out = torch.empty_like(v)
         nvox = v.numel()
-        for mode, name in ((9, "fused-2s/p0"), (8, "fused-2s/pf2"), (7, "fused-2s/4"), (6, "fused-2s"), (5, "fused-2"), (4, "strip-tma"), (3, "strip-reg"), (2, "cta-march")):
+        for mode, name in ((10, "fused-2s/l2pf"), (9, "fused-2s/p0"), (8, "fused-2s/pf2"), (7, "fused-2s/4"), (6, "fused-2s"), (5, "fused-2"), (4, "strip-tma"), (3, "strip-reg"), (2, "cta-march")):
             lib.tmb_tv_set_simple_kernels(mode)
             for half in ((False,) if mode >= 5 else (False, True)):
                 ms = timed(lambda: PD_TV_cupy(v, 3e-4, its, 0, 1, 12.0, 0, half, out=out)) / its
