@@ -165,6 +165,10 @@ int tmb_rof_tv_iter(const float *in, const float *u_in, float *u_out, int dz, in
  * ahead, 9 = 6 without the memset / copy at the start of a prox call, 10 = 6 with
  * the next plane prefetched into L2 (0 picks the measured best; same arithmetic, used by the parity tests).  Returns the old value. */
 int tmb_tv_set_simple_kernels(int enable);
+/* Debug/test switch: consumer warps per CTA and ring depth (rows in flight per warp) of the TMA-fed fused PD_TV
+ * kernel k_pd_tv3d_f2t (modes 11 / 12 of tmb_tv_set_simple_kernels; instantiated: 2x4, 3x4, 4x2, 4x4, 4x8, 5x2,
+ * anything else selects 4x4).  Returns the old setting as warps * 10 + stages. */
+int tmb_tv_set_f2t(int warps, int stages);
 /* number of kernels tmb_pd_tv launches for `iterations` iterations (PD_TV_cupy's loop,
  * regularisersCuPy.py:262-294, is one launch per iteration in the reference; here pairs of
  * iterations share a launch where the fused kernel applies).  Launch accounting of benchmarks. */

@@ -81,7 +81,7 @@ def _close(a, b):
     assert np.max(np.abs(a - b)) <= 2e-6 * max(np.max(np.abs(b)), 1.0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6, 7, 10])
 @pytest.mark.parametrize("shape,zrun,nonneg,aniso", [
     ((2, 3, 8), 2, False, False),
     ((5, 9, 124), 5, True, False),
@@ -91,7 +91,9 @@ def _close(a, b):
 ])
 def test_whole_volume_kernels_on_the_cpu(shim, plain, variant, shape, zrun, nonneg, aniso):
     """0: k_pd_tv3d_f2 (the default, validated on the B200), 1: k_pd_tv3d_f2s (run on the B200 on five
-    shapes), 2: k_pd_tv3d_f2s at four CTAs per SM, 4: with packets two rows ahead, 6: with L2 prefetches (2, 4 and 6 never ran on a GPU)."""
+    shapes), 2: k_pd_tv3d_f2s at four CTAs per SM, 4: with packets two rows ahead, 6: with L2 prefetches,
+    7 / 10: k_pd_tv3d_f2t, the TMA-fed variant with a ring of 4 / 8 stages (bulk copies as memcpy, mbarrier waits as
+    warp barriers; lanes outside the volume read NaN-poisoned stage memory and must not reach a stored lane)."""
     inp, U, P = _case(shape, sum(shape))
     U2, P2 = _two_plain(plain, inp, U, P, nonneg, aniso)
     Uo = _aligned(shape, np.nan)
@@ -111,7 +113,8 @@ def test_whole_volume_kernels_on_the_cpu(shim, plain, variant, shape, zrun, nonn
     ((10, 18, 132), [3, 7], 8, False, True),
     ((6, 5, 8), [2, 4], 1, True, False),        # every z-run starts in the neighbour's planes
 ])
-def test_z_shard_kernel_with_peer_pointers_on_the_cpu(shim, plain, shape, cuts, zrun, nonneg, aniso):
+@pytest.mark.parametrize("variant", [3, 8])
+def test_z_shard_kernel_with_peer_pointers_on_the_cpu(shim, plain, variant, shape, cuts, zrun, nonneg, aniso):
     """k_pd_tv3d_f2s<GHOST> exactly as tmb_pd_tv_iter2 launches it: every shard is its own set of arrays and
     the ghost pointers aim into the NEIGHBOURS' arrays (their last two / first two planes), like the peer
     mappings of ShardedPDTV(pairs=True).  Assembled result == two plain iterations of the whole volume."""
@@ -140,7 +143,7 @@ def test_z_shard_kernel_with_peer_pointers_on_the_cpu(shim, plain, shape, cuts, 
             ghost[9] = _ptr(hi["inp"])
         Uo = _aligned(s["U"].shape, np.nan)
         Q = [_aligned(s["U"].shape, np.nan) for _ in range(3)]
-        rc = shim.shim_run_fused_tv(3, int(nonneg), int(aniso), _ptr(s["inp"]), _ptr(s["U"]), _ptr(Uo),
+        rc = shim.shim_run_fused_tv(variant, int(nonneg), int(aniso), _ptr(s["inp"]), _ptr(s["U"]), _ptr(Uo),
                                     *[_ptr(p) for p in s["P"]], *[_ptr(q) for q in Q], SIGMA, TAU, LT, THETA, dx, dy,
                                     s["n"], zrun, int(lo is not None), int(hi is not None), *ghost)
         assert rc == 0
@@ -152,7 +155,8 @@ def test_z_shard_kernel_with_peer_pointers_on_the_cpu(shim, plain, shape, cuts, 
 
 @pytest.mark.parametrize("shape,zrun,nonneg,aniso", [((5, 9, 124), 5, True, False), ((7, 18, 132), 3, False, True),
                                                      ((4, 5, 4), 1, False, False)])
-def test_first_pass_variant_on_the_cpu(shim, plain, shape, zrun, nonneg, aniso):
+@pytest.mark.parametrize("variant", [5, 9])
+def test_first_pass_variant_on_the_cpu(shim, plain, variant, shape, zrun, nonneg, aniso):
     """k_pd_tv3d_f2s<PZERO> (hook 6's first pass of a prox call): the dual arrays are NOT read -- they hold
     NaN here -- and the input doubles as the primal variable; result == two plain iterations from P = 0."""
     inp, _, _ = _case(shape, sum(shape) + 7)
@@ -162,7 +166,7 @@ def test_first_pass_variant_on_the_cpu(shim, plain, shape, zrun, nonneg, aniso):
     Uo = _aligned(shape, np.nan)
     Q = [_aligned(shape, np.nan) for _ in range(3)]
     dz, dy, dx = shape
-    rc = shim.shim_run_fused_tv(5, int(nonneg), int(aniso), _ptr(inp), _ptr(inp), _ptr(Uo), *[_ptr(p) for p in poison],
+    rc = shim.shim_run_fused_tv(variant, int(nonneg), int(aniso), _ptr(inp), _ptr(inp), _ptr(Uo), *[_ptr(p) for p in poison],
                                 *[_ptr(q) for q in Q], SIGMA, TAU, LT, THETA, dx, dy, dz, zrun, 0, 0, *([None] * 10))
     assert rc == 0
     _close(Uo, U2)

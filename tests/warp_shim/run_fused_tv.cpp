@@ -8,11 +8,13 @@
 thread_local shim_uint3 threadIdx, blockIdx;
 thread_local ShimWarp *shim_warp = nullptr;
 thread_local int shim_lane = 0;
+std::barrier<> *shim_cta_bar = nullptr;
 
 #include "../../tomobar_b200/csrc/tmb_tv_fused.cuh"
 
 namespace tmb {
-alignas(16) unsigned char f2_smem[F2_WARPS * F2_SLOTS * 32 * sizeof(float4)];
+// lane-private slots of every warp, then (k_pd_tv3d_f2t) the TMA ring of every warp
+alignas(16) unsigned char f2_smem[f2t_smem_bytes(F2_WARPS, 8)];
 }
 
 namespace {
@@ -53,6 +55,22 @@ template <bool NN, bool AN> void lane_entry(int variant, const Args &a) {
       k_pd_tv3d_f2s<NN, AN, false, 3, 1, false, true>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau,
                                                       a.lt, a.theta, a.dx, a.dy, a.dz, a.zrun, F2Ghost<false>{});
       break;
+    case 7:
+      k_pd_tv3d_f2t<NN, AN, false, F2_WARPS, 4>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt,
+                                                a.theta, a.dx, a.dy, a.dz, a.zrun, F2Ghost<false>{});
+      break;
+    case 8:
+      k_pd_tv3d_f2t<NN, AN, true, F2_WARPS, 4>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt,
+                                               a.theta, a.dx, a.dy, a.dz, a.zrun, a.gh);
+      break;
+    case 9:
+      k_pd_tv3d_f2t<NN, AN, false, F2_WARPS, 2, true>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau,
+                                                      a.lt, a.theta, a.dx, a.dy, a.dz, a.zrun, F2Ghost<false>{});
+      break;
+    case 10:
+      k_pd_tv3d_f2t<NN, AN, false, F2_WARPS, 8>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt,
+                                                a.theta, a.dx, a.dy, a.dz, a.zrun, F2Ghost<false>{});
+      break;
     default:
       k_pd_tv3d_f2s<NN, AN, true, 3>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt, a.theta,
                                      a.dx, a.dy, a.dz, a.zrun, a.gh);
@@ -63,7 +81,8 @@ template <bool NN, bool AN> void lane_entry(int variant, const Args &a) {
 // variant: 0 k_pd_tv3d_f2, 1 k_pd_tv3d_f2s, 2 k_pd_tv3d_f2s at four CTAs per SM, 3 k_pd_tv3d_f2s<GHOST>,
 // 4 k_pd_tv3d_f2s with packets two rows ahead, 5 k_pd_tv3d_f2s<PZERO> (dual variable zero on entry, not read),
 // 6 k_pd_tv3d_f2s<L2PF> (prefetches are no-ops on the host: this checks their address arithmetic compiles and the
-//   rest of the kernel is untouched)
+//   rest of the kernel is untouched), 7 k_pd_tv3d_f2t (TMA-fed ring of 4 stages), 8 k_pd_tv3d_f2t<GHOST>,
+// 9 k_pd_tv3d_f2t<PZERO> with 2 stages, 10 k_pd_tv3d_f2t with a ring of 8 stages
 extern "C" int shim_run_fused_tv(int variant, int nonneg, int aniso, const float *in, const float *U, float *Uo,
                                  const float *P1, const float *P2, const float *P3, float *Q1, float *Q2, float *Q3,
                                  float sigma, float tau, float lt, float theta, int dx, int dy, int dz, int zrun,
@@ -76,23 +95,39 @@ extern "C" int shim_run_fused_tv(int variant, int nonneg, int aniso, const float
   a.gh.U_hi = U_hi; a.gh.P1_hi = P1_hi; a.gh.P2_hi = P2_hi; a.gh.P3_hi = P3_hi; a.gh.in_hi = in_hi;
   const int gx = (dx + tmb::F2_OUT - 1) / tmb::F2_OUT, gy = (dy + tmb::F2_S * tmb::F2_WARPS - 1) / (tmb::F2_S * tmb::F2_WARPS);
   const int gz = (dz + zrun - 1) / zrun;
+  auto lane_body = [&](int warp, int lane, int bx, int by, int bz, ShimWarp *w) {
+    threadIdx = {unsigned(warp * 32 + lane), 0, 0};
+    blockIdx = {unsigned(bx), unsigned(by), unsigned(bz)};
+    shim_warp = w;
+    shim_lane = lane;
+    if (nonneg) { if (aniso) lane_entry<true, true>(variant, a); else lane_entry<true, false>(variant, a); }
+    else { if (aniso) lane_entry<false, true>(variant, a); else lane_entry<false, false>(variant, a); }
+  };
+  const bool cta_wide = variant >= 7 && variant <= 10;  // k_pd_tv3d_f2t: consumer warps + the producer warp together
   for (int bz = 0; bz < gz; ++bz)
     for (int by = 0; by < gy; ++by)
-      for (int bx = 0; bx < gx; ++bx)
+      for (int bx = 0; bx < gx; ++bx) {
+        if (cta_wide) {
+          constexpr int NW = tmb::F2_WARPS + 1;
+          std::memset(tmb::f2_smem, 0xff, sizeof(tmb::f2_smem));  // NaN-poison the slots and the ring
+          std::barrier<> cta_bar(NW * 32);
+          shim_cta_bar = &cta_bar;
+          std::vector<ShimWarp> warps(NW);
+          std::vector<std::thread> lanes;
+          for (int warp = 0; warp < NW; ++warp)
+            for (int lane = 0; lane < 32; ++lane)
+              lanes.emplace_back([&, warp, lane] { lane_body(warp, lane, bx, by, bz, &warps[warp]); });
+          for (auto &t : lanes) t.join();
+          continue;
+        }
         for (int warp = 0; warp < tmb::F2_WARPS; ++warp) {
           std::memset(tmb::f2_smem, 0xff, sizeof(tmb::f2_smem));  // NaN-poison the slots
           ShimWarp w;
           std::vector<std::thread> lanes;
           for (int lane = 0; lane < 32; ++lane)
-            lanes.emplace_back([&, lane] {
-              threadIdx = {unsigned(warp * 32 + lane), 0, 0};
-              blockIdx = {unsigned(bx), unsigned(by), unsigned(bz)};
-              shim_warp = &w;
-              shim_lane = lane;
-              if (nonneg) { if (aniso) lane_entry<true, true>(variant, a); else lane_entry<true, false>(variant, a); }
-              else { if (aniso) lane_entry<false, true>(variant, a); else lane_entry<false, false>(variant, a); }
-            });
+            lanes.emplace_back([&, warp, lane] { lane_body(warp, lane, bx, by, bz, &w); });
           for (auto &t : lanes) t.join();
         }
+      }
   return 0;
 }

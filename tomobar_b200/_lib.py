@@ -46,6 +46,7 @@ SIGNATURES = {
     "tmb_pd_tv_iter2": (_i, [_fp] * 9 + [_i, _i, _i, _f, _i, _i, _f, _i, _i] + [_fp] * 10 + [_vp]),
     "tmb_rof_tv_iter": (_i, [_fp, _fp, _fp, _i, _i, _i, _f, _f, _i, _i, _i, _fp, _fp, _vp]),
     "tmb_tv_set_simple_kernels": (_i, [_i]),
+    "tmb_tv_set_f2t": (_i, [_i, _i]),
     "tmb_pd_tv_launches": (_i, [_i, _i, _i, _i, _i]),
     "tmb_fista_grad_step": (_i, [_fp, _fp, _fp, _sz, _f, _i, _vp]),
     "tmb_fista_momentum": (_i, [_fp, _fp, _fp, _sz, _f, _vp]),

@@ -66,6 +66,20 @@ constexpr int FQ_MIN_NZ = 17;     // smaller stacks keep the 8-slice kernel
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: one flag per device for each call site
+// (a process that reconstructs on cuda:0 and then on cuda:1 must opt in to the large shared memory twice)
+struct PerDeviceOnce {
+  unsigned long long done = 0;  // bit d: device d (mod 64) has been set up
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+
 struct GeomDims {
   int nz, n, nu, na;
   int nzc;   // z-chunks allocated (multiple of NZC)
@@ -114,6 +128,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
     if (spins > (1u << 22)) __trap();
 }
+// plain spin on an mbarrier phase (no watchdog: used where the wait sits in a hot unrolled loop)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// L2 eviction policy "keep": for rows that a neighbouring warp / CTA re-reads a few microseconds later
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+template <bool HINT>
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                              uint64_t pol) {
+  if constexpr (HINT) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+  } else {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+// orders earlier generic-proxy accesses of shared memory (LDS / STS) before later async-proxy ones (TMA writes)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -766,12 +766,11 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
   const size_t smem = sizeof(float4) * FP_STAGES * FP_G * NZC * FP_W;
   const size_t smem_q1 = sizeof(float4) * FQ_STAGES * FQ_G * FQ_W * FQ_CG;
   const size_t smem_q2 = sizeof(float4) * FQ_STAGES * FQ_G2 * 2 * FQ_W * FQ_CG;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fpq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q1));
     TMB_CUDA_CHECK(cudaFuncSetAttribute(k_fpq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q2));
-    attr_set = true;
   }
   int j = 0;
   while (j < na_loc) {

@@ -8,6 +8,8 @@ from tomobar_b200._lib import lib
 
 # TMB_TV_HOOK=<0..8> selects the PD_TV kernel family (tmb_tv_set_simple_kernels), e.g. 6 = k_pd_tv3d_f2s
 lib.tmb_tv_set_simple_kernels(int(os.environ.get("TMB_TV_HOOK", "0")))
+if os.environ.get("TMB_F2T_CFG"):
+    lib.tmb_tv_set_f2t(*[int(v) for v in os.environ["TMB_F2T_CFG"].split()])
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 nz = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
