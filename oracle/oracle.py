@@ -29,16 +29,19 @@ _LIB = None
 f32 = np.float32
 
 
+_SOURCES = ("proj_oracle.c", "tv_oracle.c", "fbp2d_oracle.c")
+
+
 def build(force: bool = False) -> str:
-    """Compile proj_oracle.c -> oracle/_build/liboracle.so (gcc -O2 -fopenmp)."""
+    """Compile the C restatements -> oracle/_build/liboracle.so (gcc -O2 -fopenmp)."""
     so = os.path.join(_BUILD, "liboracle.so")
-    src = os.path.join(_HERE, "proj_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in _SOURCES]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         os.makedirs(_BUILD, exist_ok=True)
         # -ffp-contract=off: every fused multiply-add in the oracle is an explicit fmaf()
         subprocess.check_call(
             ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
-             "-o", so, src, "-lm"]
+             "-o", so] + srcs + ["-lm"]
         )
     return so
 
@@ -52,6 +55,15 @@ def _lib():
             fn = getattr(_LIB, name)
             fn.restype = None
             fn.argtypes = [fp, fp, fp] + [ctypes.c_int] * 5
+        ci, cf = ctypes.c_int, ctypes.c_float
+        _LIB.oracle_pd_tv.restype = ci
+        _LIB.oracle_pd_tv.argtypes = [fp, fp, ci, ci, ci, cf, cf, cf, cf, ci, ci, ci]
+        _LIB.oracle_rof_tv.restype = ci
+        _LIB.oracle_rof_tv.argtypes = [fp, fp, ci, ci, ci, cf, ci, cf]
+        _LIB.oracle_bp2d_line.restype = None
+        _LIB.oracle_bp2d_line.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), ci, ci, ci, ci]
+        _LIB.oracle_threads.restype = ci
+        _LIB.oracle_threads.argtypes = []
     return _LIB
 
 
@@ -236,9 +248,17 @@ def _bwd0(P, axis):
     return P - prv
 
 
+def threads() -> int:
+    """OpenMP threads the C restatements run on (what ``cores`` of a CPU baseline reports)."""
+    return int(_lib().oracle_threads())
+
+
 def pd_tv(data, regularisation_parameter=1e-5, iterations=1000, methodTV=0, nonneg=0,
-          lipschitz_const=8.0, half_precision=False):
-    """regularisersCuPy.py:170-296 + primal_dual_for_total_variation.cu:126-261 / :361-492."""
+          lipschitz_const=8.0, half_precision=False, use_c=True):
+    """regularisersCuPy.py:170-296 + primal_dual_for_total_variation.cu:126-261 / :361-492.
+
+    ``use_c`` (fp32 duals): the OpenMP twin in tv_oracle.c, bit-identical to the numpy statements below
+    (tests/test_oracle_tv_c.py) -- the numpy version is single-threaded."""
     data = np.asarray(data)
     if data.dtype != np.float32:
         raise ValueError("The input data should be float32 data type")
@@ -248,6 +268,14 @@ def pd_tv(data, regularisation_parameter=1e-5, iterations=1000, methodTV=0, nonn
     theta = f32(1.0)
     lt = f32(tau / regularisation_parameter)
     nd = data.ndim
+    if use_c and not half_precision:
+        src = np.ascontiguousarray(data)
+        shp = (1,) * (3 - nd) + src.shape
+        out = np.empty_like(src)
+        if _lib().oracle_pd_tv(_ptr(src), _ptr(out), shp[0], shp[1], shp[2], float(tau), float(sigma), float(lt),
+                               float(theta), int(iterations), int(methodTV), int(nonneg)) != 0:
+            raise MemoryError("oracle_pd_tv")
+        return np.expand_dims(out, ax) if is2d else out
     U = data.copy()
     pdt = np.float16 if half_precision else np.float32
     P = [np.zeros(data.shape, dtype=pdt) for _ in range(nd)]
@@ -282,8 +310,9 @@ def _refl_prev(U, axis):
 
 
 def rof_tv(data, regularisation_parameter=1e-5, iterations=3000, time_marching_parameter=0.001,
-           half_precision=False):
-    """regularisersCuPy.py:41-167 + rudin_osher_fatemi_total_variation.cu:70-148, 157-248."""
+           half_precision=False, use_c=True):
+    """regularisersCuPy.py:41-167 + rudin_osher_fatemi_total_variation.cu:70-148, 157-248.
+    ``use_c``: as for ``pd_tv``."""
     data = np.asarray(data)
     if data.dtype != np.float32:
         raise ValueError("The input data should be float32 data type")
@@ -291,6 +320,14 @@ def rof_tv(data, regularisation_parameter=1e-5, iterations=3000, time_marching_p
     nd = data.ndim
     lam = f32(regularisation_parameter)
     tau = f32(time_marching_parameter)
+    if use_c and not half_precision:
+        src = np.ascontiguousarray(data)
+        shp = (1,) * (3 - nd) + src.shape
+        out = np.empty_like(src)
+        if _lib().oracle_rof_tv(_ptr(src), _ptr(out), shp[0], shp[1], shp[2], float(lam), int(iterations),
+                                float(tau)) != 0:
+            raise MemoryError("oracle_rof_tv")
+        return np.expand_dims(out, ax) if is2d else out
     ddt = np.float16 if half_precision else np.float32
     U = data.copy()
     for _ in range(iterations):
@@ -379,6 +416,54 @@ def filtersinc3d(proj: np.ndarray, cutoff: float) -> np.ndarray:
     pf *= f
     # irfft(norm="forward") applies no scaling on the inverse
     return (np.fft.irfft(pf, nu, axis=-1) * nu).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# the reference's CPU direct method for 2-D data (BASELINE.json config 1): methodsDIR.py:121-175, 295-320
+# --------------------------------------------------------------------------------------
+def filtersinc2d(sinogram: np.ndarray) -> np.ndarray:
+    """methodsDIR.py:295-320: the numpy sinc filter of the CPU class (cut-off a = 1.1 hard-coded, full
+    complex FFT per projection, scaled by 1 / number of projections)."""
+    a = 1.1
+    na, nu = sinogram.shape
+    w = np.linspace(-np.pi, np.pi - (2 * np.pi) / nu, nu, dtype="float32")
+    half = a * w / 2.0
+    ramp = np.abs(2.0 / a * np.sin(half))
+    # np.dot(rn2, pinv(rd as a 1 x n matrix)) == sum(sin(rd) * rd) / sum(rd^2)
+    kappa = np.dot(np.sin(half), np.linalg.pinv(half.astype(np.float64)[None, :]))
+    f = np.fft.fftshift(ramp * kappa ** 2)
+    out = np.zeros(sinogram.shape)
+    for i in range(na):
+        out[i, :] = (1.0 / na) * np.real(np.fft.ifft(np.fft.fft(sinogram[i, :]) * f))
+    return np.float32(out)
+
+
+def parallel2d_vectors(angles: np.ndarray) -> np.ndarray:
+    """[na, 6] (ray, detector centre, u) of ASTRA's classic "parallel" 2-D geometry, which is what the CPU
+    class builds (astra_base.py:224-232: create_proj_geom("parallel", 1.0, detectors, angles); the centre of
+    rotation is not part of it).  Same convention as supp/funcs.py:22-43 with a zero offset."""
+    t = np.asarray(angles, dtype=np.float32).astype(np.float64)
+    v = np.zeros((t.size, 6))
+    v[:, 0], v[:, 1] = np.sin(t), -np.cos(t)
+    v[:, 4], v[:, 5] = np.cos(t), np.sin(t)
+    return v
+
+
+def bp2d_line(sinogram: np.ndarray, angles: np.ndarray, n: int, threads: int = 1) -> np.ndarray:
+    """ASTRA's CPU ``BP`` with the ``line`` projector (fbp2d_oracle.c); image row 0 is the TOP row."""
+    sinogram = np.ascontiguousarray(sinogram, dtype=np.float32)
+    na, nu = sinogram.shape
+    vec = np.ascontiguousarray(parallel2d_vectors(angles))
+    out = np.empty((n, n), np.float32)
+    _lib().oracle_bp2d_line(_ptr(sinogram), _ptr(out), vec.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                            int(n), int(nu), int(na), int(threads))
+    return out
+
+
+def fbp2d_cpu(sinogram: np.ndarray, angles: np.ndarray, n: int, pad: int = 0, threads: int = 1) -> np.ndarray:
+    """``RecToolsDIR(device_projector="cpu").FBP`` for 2-D data [angles, detX] (methodsDIR.py:161-168)."""
+    data = pad_detector(np.asarray(sinogram, dtype=np.float32), pad)
+    return bp2d_line(filtersinc2d(data), angles, n, threads)
 
 
 # --------------------------------------------------------------------------------------

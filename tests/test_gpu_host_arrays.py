@@ -7,10 +7,7 @@ import numpy as np
 import pytest
 from numpy.testing import assert_allclose
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("TMB_TEST_UNVALIDATED"),
-                                 reason="host-array wrappers written after round 1's GPU budget ended (plumbing over "
-                                        "the validated RecToolsDIRCuPy path); first run in round 2")]
+pytestmark = [pytest.mark.gpu]
 
 LABELS = ["angles", "detY", "detX"]
 

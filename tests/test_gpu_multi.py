@@ -36,15 +36,16 @@ def _worker(rank, world, init_file, results):
         for peer, sync in ((True, "signals"), (True, "barrier"), (False, "signals")):
             # halos read over NVLink inside the kernel (two ways of ordering the iterations) / sent as messages
             for half in (False, True):
-                tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half, peer_memory=peer, sync=sync)
+                tv = ShardedPDTV(sh, (sh.nz_local, n, n), dev, half, peer_memory=peer, sync=sync, pairs=False)
                 with single_iteration_tv():
                     whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, half)
                 for _ in range(2):  # buffers are reused across calls
                     part = tv(full[sh.z0:sh.z1].contiguous(), 4e-4, 9, 0, 1, 12.0)
                     out[f"tv_equal_half{int(half)}"] &= bool(torch.equal(sh.all_gather_volume(part), whole))
-            if peer and os.environ.get("TMB_TEST_UNVALIDATED"):
-                # pairs of iterations per pass over peer memory (not yet run on hardware, see ShardedPDTV)
-                tvp = ShardedPDTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=True, sync=sync, pairs=True)
+            if peer:
+                # pairs of iterations per pass over peer memory (the default of ShardedPDTV for fp32 duals)
+                tvp = ShardedPDTV(sh, (sh.nz_local, n, n), dev, False, peer_memory=True, sync=sync)
+                assert tvp.pairs
                 with single_iteration_tv():
                     whole = PD_TV_cupy(full, 4e-4, 9, 0, 1, 12.0, rank, False)
                 for _ in range(2):
@@ -62,6 +63,7 @@ def _worker(rank, world, init_file, results):
         reg = {"method": "PD_TV", "regul_param": 3e-4, "iterations": 6}
         rec = RecToolsIRCuPy(n, 0, sh.nz_local, 0.0, angles, n, rank, 4)
         rec.set_zshard(sh)
+        rec.tv_pairs = False  # one iteration per launch on both sides: bit for bit
         x_loc = rec.FISTA({"projection_data": sino[sh.z0:sh.z1].contiguous()}, dict(alg), dict(reg))
         x_all = sh.all_gather_volume(x_loc.contiguous())
         with single_iteration_tv():
@@ -69,6 +71,13 @@ def _worker(rank, world, init_file, results):
                                                                           dict(reg))
         out["fista_equal"] = bool(torch.equal(x_all, ref))
         out["fista_maxdiff"] = float((x_all - ref).abs().max())
+        # the defaults on both sides: pairs of iterations per pass, sharded (peer memory) and whole-volume
+        rec.tv_pairs = None
+        rec.set_zshard(sh)
+        x_all = sh.all_gather_volume(rec.FISTA({"projection_data": sino[sh.z0:sh.z1].contiguous()}, dict(alg),
+                                               dict(reg)).contiguous())
+        ref = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, rank, 4).FISTA({"projection_data": sino}, dict(alg), dict(reg))
+        out["fista_pairs_maxdiff"] = float((x_all - ref).abs().max() / ref.abs().max())
         # --- sharded ADMM-OS + ROF_TV == whole-volume run (BASELINE.json config 3 in miniature) ----------
         aalg = {"iterations": 3, "lipschitz_const": 2000.0, "ADMM_rho_const": 1.0, "ADMM_relax_par": 1.7,
                 "recon_mask_radius": None}
@@ -99,6 +108,7 @@ def test_multi_gpu_sharded_tv_and_fista(world):
         assert res["rof_equal"], res
         assert res["fista_equal"], res
         assert res["admm_equal"], res
-        assert res.get("tv_pairs_maxdiff", 0.0) < 2e-6, res
+        assert res["tv_pairs_maxdiff"] < 2e-6, res
+        assert res["fista_pairs_maxdiff"] < 2e-6, res
         assert res["L_sharded"] == pytest.approx(res["L_whole"], rel=1e-3)
     assert all(results[r]["L_sharded"] == results[0]["L_sharded"] for r in range(world))

@@ -135,11 +135,7 @@ def test_split_variant_of_the_fused_kernel(shape):
         assert np.isfinite(a).all() and rel_max(a, b) < 2e-6
 
 
-@pytest.mark.skipif(not os.environ.get("TMB_TEST_UNVALIDATED"),
-                    reason="hooks 7 - 10 (split fused kernel at four CTAs per SM / packets two rows ahead / no initial memset / L2 prefetch) were "
-                           "written after the round's GPU budget ended (their source runs on the CPU warp shim); "
-                           "first GPU run in round 2")
-@pytest.mark.parametrize("mode", [7, 8, 9, 10])
+@pytest.mark.parametrize("mode", [0, 5, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("shape", [(9, 21, 244), (66, 37, 364), (2, 2, 4), (7, 18, 132)])
 def test_untimed_variants_of_the_fused_kernel(shape, mode):
     from tomobar_b200._lib import lib

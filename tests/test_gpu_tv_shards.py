@@ -231,10 +231,6 @@ def _sharded_prox_pairs(v, cuts, lam, iters, methodTV, nonneg, lip):
     return torch.cat([s["U"][a][2:s["nzl"] + 2] for s in S], dim=0)
 
 
-@pytest.mark.skipif(not os.environ.get("TMB_TEST_UNVALIDATED"),
-                    reason="tmb_pd_tv_iter2 (fused pairs of PD_TV iterations on z-shards) was written after the "
-                           "round's GPU budget ended: its index logic is verified by the CPU emulation "
-                           "(tests/test_pd_fused2_emulation.py), its first GPU run is round 2's first item")
 @pytest.mark.parametrize("shape,cuts", [((40, 36, 64), [20]), ((45, 21, 132), [8, 30]), ((70, 16, 260), [2, 36]),
                                         ((96, 8, 128), [48])])
 @pytest.mark.parametrize("methodTV,nonneg,iters", [(0, 1, 6), (1, 0, 7)])

@@ -126,7 +126,8 @@ def test_sharded_pairs_end_to_end_on_the_cpu(shim, plain, monkeypatch, nz_total,
             z0, z1 = zs.shard_bounds(nz_total, world, rank, 2)
             shard = SimpleNamespace(nz_total=nz_total, world=world, multiple=2, rank=rank, group=None, z0=z0, z1=z1,
                                     nz_local=z1 - z0, prev=rank - 1 if rank > 0 else None,
-                                    next=rank + 1 if rank + 1 < world else None, _global=lambda p: p)
+                                    next=rank + 1 if rank + 1 < world else None, _global=lambda p: p,
+                                        require_tv_shards=lambda what="": None)
             tv = zs.ShardedPDTV(shard, (z1 - z0, ny, nx), rank, False, peer_memory=True, sync="signals", pairs=True)
             assert tv.pairs
             data = torch.from_numpy(np.ascontiguousarray(vol[z0:z1]))

@@ -151,3 +151,25 @@ def test_peer_pointers_of_a_fused_pass():
         u_lo1, p_lo1, u_hi1 = make(1)._ghost_ptrs(a)
         assert g[0] == u_lo1 - plane * 4 and g[5] == u_hi1
         assert g[1:4] == [p - plane * 4 for p in p_lo1]
+
+
+def test_shard_decisions_are_collective():
+    """What must be the same on every rank comes from the table of ALL blocks (an odd slice count left
+    the last rank with one slice and on a different code path than its neighbours, which then waited forever)."""
+    from tomobar_b200.zshard import ZShard, shard_table
+
+    with pytest.raises(ValueError, match="own no slices"):
+        shard_table(6, 4)  # blocks of 2, 2, 2, 0: every rank raises, not only rank 3
+    assert shard_table(5, 2) == [(0, 4), (4, 5)]
+    # the one-slice last block: every rank refuses the sharded 3-D TV with the same error
+    for rank in range(2):
+        sh = ZShard.__new__(ZShard)
+        sh.rank, sh.world, sh.nz_total, sh.multiple = rank, 2, 5, 2
+        sh.bounds = shard_table(5, 2)
+        sh.sizes = [b - a for a, b in sh.bounds]
+        assert sh.min_size == 1
+        with pytest.raises(ValueError, match="at least two slices per rank"):
+            sh.require_tv_shards("PD_TV")
+    sh.world, sh.nz_total, sh.bounds = 2, 8, shard_table(8, 2)
+    sh.sizes = [4, 4]
+    sh.require_tv_shards()

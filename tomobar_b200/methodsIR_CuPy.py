@@ -87,7 +87,7 @@ class RecToolsIRCuPy:
         self.zshard = None   # set_zshard(): this object reconstructs one z-block of a larger volume
         self.tv_peer_memory = None  # sharded TV halos: None = NVLink peer loads on NCCL, False = messages
         self.tv_sync = "signals"    # peer-memory ordering: pairwise semaphores, or "barrier"
-        self.tv_pairs = None        # sharded PD_TV: two iterations per pass (None: TMB_SHARDED_PAIRS, off by default)
+        self.tv_pairs = None        # sharded PD_TV: two iterations per pass (None: on unless TMB_SHARDED_PAIRS=0)
         self._sharded_tv = {}
 
     def set_zshard(self, shard) -> None:
@@ -271,7 +271,10 @@ class RecToolsIRCuPy:
         """``prox_regul`` (regularisersCuPy.py:6-38) writing into a preallocated volume."""
         dev = self.Atools.device_index
         sh = self.zshard
-        sharded3d = sh is not None and sh.world > 1 and X.ndim == 3 and min(X.shape) > 1
+        # the same decision on every rank: taken from the GLOBAL slice count and the in-plane shape, never from
+        # this rank's block (a one-slice last block must not send one rank down the local 2-D path while its
+        # neighbours wait for it; ZShard.require_tv_shards raises on all ranks instead)
+        sharded3d = sh is not None and sh.world > 1 and X.ndim == 3 and sh.nz_total > 1 and min(X.shape[1:]) > 1
         if "ROF_TV" in reg["method"]:
             if sharded3d:
                 from tomobar_b200.zshard import ShardedROFTV
@@ -447,5 +450,6 @@ class RecToolsIRCuPy:
                 backproj = self._Atb(proj_data / Ax, sub_ind, use_os)
                 x = x * (backproj * normalisation)
                 if _regularisation_upd_["method"] is not None:
-                    x = prox_regul(self, x, _regularisation_upd_)
+                    # through _prox_into: whole-volume TV also when this object holds one z-shard
+                    x = self._prox_into(x.contiguous(), _regularisation_upd_, torch.empty_like(x))
         return self._finish(x, _algorithm_upd_["recon_mask_radius"])

@@ -40,6 +40,16 @@ def shard_bounds(nz: int, world: int, rank: int, multiple: int = 2) -> Tuple[int
     return z0, min(nz, z0 + per)
 
 
+def shard_table(nz: int, world: int, multiple: int = 2) -> List[Tuple[int, int]]:
+    """The blocks of all ranks.  Raises when a rank would own no slices -- the same error on EVERY rank, because
+    every rank evaluates the same table (one rank raising alone would leave the others waiting in a collective)."""
+    bounds = [shard_bounds(nz, world, r, multiple) for r in range(world)]
+    empty = [r for r, (a, b) in enumerate(bounds) if b <= a]
+    if empty:
+        raise ValueError(f"ranks {empty} of {world} would own no slices of {nz}: use fewer ranks")
+    return bounds
+
+
 class ZShard:
     """The z-partition of one rank and the collectives the hot path needs."""
 
@@ -51,9 +61,11 @@ class ZShard:
             self.rank, self.world = 0, 1
         self.nz_total = int(nz_total)
         self.multiple = multiple
-        self.z0, self.z1 = shard_bounds(self.nz_total, self.world, self.rank, multiple)
-        if self.z1 <= self.z0:
-            raise ValueError(f"rank {self.rank} of {self.world} owns no slices of {nz_total}: use fewer ranks")
+        # every rank knows every rank's block: decisions that must be the same everywhere (is a rank empty,
+        # can the 3-D TV prox run across the shards) are taken from this table, never from the local shape
+        self.bounds = shard_table(self.nz_total, self.world, multiple)
+        self.sizes = [b[1] - b[0] for b in self.bounds]
+        self.z0, self.z1 = self.bounds[self.rank]
         # neighbours that own slices (trailing ranks may be empty only if the constructor raised there)
         self.prev = self.rank - 1 if self.rank > 0 else None
         self.next = self.rank + 1 if self.rank + 1 < self.world and self.z1 < self.nz_total else None
@@ -61,6 +73,20 @@ class ZShard:
     @property
     def nz_local(self) -> int:
         return self.z1 - self.z0
+
+    @property
+    def min_size(self) -> int:
+        """Slices of the smallest shard (the same number on every rank)."""
+        return min(self.sizes)
+
+    def require_tv_shards(self, what: str = "3-D TV") -> None:
+        """The sharded TV kernels need >= 2 planes in EVERY shard (an odd ``nz_total`` can leave the last rank
+        with one).  The check uses the global table, so all ranks raise together instead of one rank taking a
+        different path and the others waiting for it in a rendezvous / semaphore."""
+        if self.world > 1 and self.min_size < 2:
+            raise ValueError(f"{what} across z-shards needs at least two slices per rank; {self.nz_total} slices "
+                             f"over {self.world} ranks give blocks of {self.sizes}: use fewer ranks or an even "
+                             "number of slices")
 
     def _global(self, peer: int) -> int:
         return dist.get_global_rank(self.group, peer) if self.group is not None else peer
@@ -204,11 +230,11 @@ class ShardedPDTV:
     * ``peer_memory=False``: ghost planes next to the shard, refreshed with point-to-point messages
       (5 planes per rank per iteration) before each launch.
 
-    ``pairs=True`` (peer memory, fp32 duals; opt-in, also ``TMB_SHARDED_PAIRS=1``): two iterations per
-    pass through ``tmb_pd_tv_iter2`` -- the kernel reaches two planes into each neighbour (U, P1..P3
-    and the prox input, which then lives in symmetric memory too) and the neighbours synchronise once
-    per PAIR of iterations.  NOT yet run on hardware (written after round 1's GPU budget ended; the
-    kernel's index logic is covered by tests/test_pd_fused2_emulation.py): hence off by default.
+    ``pairs`` (default with peer memory and fp32 duals; ``pairs=False`` or ``TMB_SHARDED_PAIRS=0`` turn it
+    off): two iterations per pass through ``tmb_pd_tv_iter2`` -- the kernel reaches two planes into each
+    neighbour (U, P1..P3 and the prox input, which then lives in symmetric memory too) and the neighbours
+    synchronise once per PAIR of iterations.  Same arithmetic as the whole-volume prox, which pairs its
+    iterations in the same kernel (tests/test_gpu_tv_shards.py, tests/test_gpu_multi.py).
 
     Buffers are allocated once and reused across calls."""
 
@@ -219,12 +245,11 @@ class ShardedPDTV:
             raise ValueError("ShardedPDTV: the volume shard does not match the z-partition")
         self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
         self.peer = _peer_memory_default(shard, device) if peer_memory is None else bool(peer_memory)
+        shard.require_tv_shards("PD_TV")
         if pairs is None:
-            pairs = os.environ.get("TMB_SHARDED_PAIRS", "0") == "1"
-        # pairs of iterations: peer memory, fp32 duals, rows of whole float4s, every shard >= 2 planes
-        self.pairs = bool(pairs) and self.peer and not self.half and nx % 4 == 0 and ny >= 2 and \
-            min(shard_bounds(shard.nz_total, shard.world, r, shard.multiple)[1] -
-                shard_bounds(shard.nz_total, shard.world, r, shard.multiple)[0] for r in range(shard.world)) >= 2
+            pairs = os.environ.get("TMB_SHARDED_PAIRS", "1") != "0"
+        # pairs of iterations: peer memory, fp32 duals, rows of whole float4s (every shard has >= 2 planes)
+        self.pairs = bool(pairs) and self.peer and not self.half and nx % 4 == 0 and ny >= 2
         pdt = torch.float16 if self.half else torch.float32
         # U: ghost plane below (index 0) and above (index nzl + 1); P: ghost plane below only
         if not self.peer:
@@ -385,8 +410,7 @@ class ShardedROFTV:
         nzl, ny, nx = shape
         if nzl != shard.nz_local:
             raise ValueError("ShardedROFTV: the volume shard does not match the z-partition")
-        if shard.world > 1 and nzl < 2:
-            raise ValueError("ShardedROFTV: every shard needs at least two slices")
+        shard.require_tv_shards("ROF_TV")
         self.shard, self.shape, self.device, self.half = shard, (nzl, ny, nx), device, bool(half_precision)
         self.peer = _peer_memory_default(shard, device) if peer_memory is None else bool(peer_memory)
         if not self.peer:
