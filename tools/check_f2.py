@@ -37,7 +37,7 @@ def main():
         v = torch.randn(nz, n, n, device="cuda") * 0.02
         out = torch.empty_like(v)
         ref = None
-        for mode, name in ((3, "strip-reg"), (5, "fused-2"), (6, "fused-2s"), (7, "fused-2s/4"), (8, "fused-2s/pf2"), (9, "fused-2s/p0"), (10, "fused-2s/l2pf"), (13, "fused-2s/p0+l2pf"), (0, "default")):
+        for mode, name in ((3, "strip-reg"), (5, "fused-2"), (6, "fused-2s"), (7, "fused-2s/4"), (8, "fused-2s/pf2"), (9, "fused-2s/p0"), (10, "fused-2s/l2pf"), (13, "fused-2s/p0+l2pf"), (0, "default"), (14, "DIAG mem-only"), (15, "DIAG L2-resident")):
             run(mode, v, its, out)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
