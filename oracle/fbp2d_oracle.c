@@ -36,6 +36,14 @@ int oracle_threads(void) {
 #endif
 }
 
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static void bp_angle(const float *srow, float *vol, const double *v, int n, int nu) {
   const double rayX = v[0], rayY = v[1], uX = v[4], uY = v[5];
   const double detSX = v[2] - 0.5 * (double)nu * uX, detSY = v[3] - 0.5 * (double)nu * uY;

@@ -64,6 +64,8 @@ def _lib():
         _LIB.oracle_bp2d_line.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), ci, ci, ci, ci]
         _LIB.oracle_threads.restype = ci
         _LIB.oracle_threads.argtypes = []
+        _LIB.oracle_set_threads.restype = None
+        _LIB.oracle_set_threads.argtypes = [ci]
     return _LIB
 
 
@@ -251,6 +253,12 @@ def _bwd0(P, axis):
 def threads() -> int:
     """OpenMP threads the C restatements run on (what ``cores`` of a CPU baseline reports)."""
     return int(_lib().oracle_threads())
+
+
+def set_threads(n: int) -> int:
+    """Size the OpenMP pool explicitly (an inherited OMP_NUM_THREADS=1, e.g. from torchrun, must not decide it)."""
+    _lib().oracle_set_threads(int(n))
+    return threads()
 
 
 def pd_tv(data, regularisation_parameter=1e-5, iterations=1000, methodTV=0, nonneg=0,
