@@ -141,7 +141,11 @@ int tmb_pd_tv_iter(const float *in, const float *u_in, float *u_out, const void 
  * planes dz and dz+1 of u_in and plane dz of p1_in..p3_in and `in`.  u_lo / p*_lo point at plane -2,
  * in_lo at plane -1, u_hi / p*_hi / in_hi at plane dz (NULL = adjacent memory; peer pointers allowed
  * as for tmb_pd_tv_iter).  Needs dx % 4 == 0, 16-byte aligned arrays and shards of >= 2 planes
- * (TMB_ERR_UNSUPPORTED otherwise).  Same arithmetic as two tmb_pd_tv_iter calls.                  */
+ * (TMB_ERR_UNSUPPORTED otherwise).  Same arithmetic as two tmb_pd_tv_iter calls.
+ * p1_in == p2_in == p3_in == NULL: the dual variable is zero everywhere (the first pair of a prox call,
+ * regularisersCuPy.py:219-223 allocates it as zeros): it is read neither here nor in the ghost planes, and u_in may
+ * then be the prox input itself (u_lo / u_hi: the neighbours' inputs), which saves the caller the copy of the input
+ * into the primal buffer and the three memsets.                                                                    */
 int tmb_pd_tv_iter2(const float *in, const float *u_in, float *u_out, const float *p1_in, const float *p2_in,
                     const float *p3_in, float *p1_out, float *p2_out, float *p3_out, int dz, int dy, int dx,
                     float regularisation_parameter, int methodTV, int nonneg, float lipschitz_const,

@@ -177,7 +177,7 @@ def test_explicit_ghost_pointers(half):
 
 
 # ---- pairs of iterations per pass (tmb_pd_tv_iter2) -------------------------------------------------
-def _sharded_prox_pairs(v, cuts, lam, iters, methodTV, nonneg, lip):
+def _sharded_prox_pairs(v, cuts, lam, iters, methodTV, nonneg, lip, pzero_first=False):
     """z-blocks advanced in lock step, two iterations per pass: U keeps two ghost planes on either side,
     P two below and one above, Input one on either side (adjacent memory, refreshed by copies once per
     PAIR); an odd last iteration goes through tmb_pd_tv_iter on the same buffers."""
@@ -219,7 +219,9 @@ def _sharded_prox_pairs(v, cuts, lam, iters, methodTV, nonneg, lip):
             U, P, D, nzl = s["U"], s["P"], s["D"], s["nzl"]
             lo, hi = int(i > 0), int(i + 1 < len(S))
             if pair:
-                check(lib.tmb_pd_tv_iter2(ptr(D[1:]), ptr(U[a][2:]), ptr(U[b][2:]), *[ptr(P[a][c][2:]) for c in range(3)],
+                # the first pair of a prox call may be told that the dual variable is zero (it is then not read)
+                p_in = [None] * 3 if (pzero_first and it == 0) else [ptr(P[a][c][2:]) for c in range(3)]
+                check(lib.tmb_pd_tv_iter2(ptr(D[1:]), ptr(U[a][2:]), ptr(U[b][2:]), *p_in,
                                           *[ptr(P[b][c][2:]) for c in range(3)], nzl, ny, nx, lam, methodTV, nonneg,
                                           lip, lo, hi, *([None] * 10), stream_ptr(v)), "tmb_pd_tv_iter2")
             else:
@@ -240,6 +242,7 @@ def test_sharded_pairs_of_pd_iterations(shape, cuts, methodTV, nonneg, iters):
     v = _vol(shape, 17)
     with single_iteration_tv():
         whole = PD_TV_cupy(v, 4e-4, iters, methodTV, nonneg, 12.0, 0, False)
-    parts = _sharded_prox_pairs(v, list(cuts), 4e-4, iters, methodTV, nonneg, 12.0)
-    torch.cuda.synchronize()
-    assert rel_max(parts.cpu().numpy(), whole.cpu().numpy()) < 2e-6
+    for pzero_first in (False, True):
+        parts = _sharded_prox_pairs(v, list(cuts), 4e-4, iters, methodTV, nonneg, 12.0, pzero_first)
+        torch.cuda.synchronize()
+        assert rel_max(parts.cpu().numpy(), whole.cpu().numpy()) < 2e-6

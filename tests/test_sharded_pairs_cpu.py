@@ -86,7 +86,8 @@ def test_sharded_pairs_end_to_end_on_the_cpu(shim, plain, monkeypatch, nz_total,
         ghosts, s = rest[:10], _scalars(lam_, lip_)
         cast = lambda a: C.cast(int(a), FP) if a else None  # noqa: E731
         with shim_lock:  # the shim keeps its shared memory in one global array
-            rc = shim.shim_run_fused_tv(3, int(nn), int(method), *[cast(a) for a in (inp, u_in, u_out, p1i, p2i, p3i, p1o, p2o, p3o)],
+            variant = 11 if not p1i else 3  # no dual inputs: the first pair of a prox call (PZERO)
+            rc = shim.shim_run_fused_tv(variant, int(nn), int(method), *[cast(a) for a in (inp, u_in, u_out, p1i, p2i, p3i, p1o, p2o, p3o)],
                                         *s, dx, dy, dz, max(1, (dz + 1) // 2), int(glo), int(ghi), *[cast(g) for g in ghosts])
         return rc
 

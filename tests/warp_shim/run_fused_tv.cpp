@@ -71,6 +71,10 @@ template <bool NN, bool AN> void lane_entry(int variant, const Args &a) {
       k_pd_tv3d_f2t<NN, AN, false, F2_WARPS, 8>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt,
                                                 a.theta, a.dx, a.dy, a.dz, a.zrun, F2Ghost<false>{});
       break;
+    case 11:
+      k_pd_tv3d_f2s<NN, AN, true, 3, 1, true>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt,
+                                              a.theta, a.dx, a.dy, a.dz, a.zrun, a.gh);
+      break;
     default:
       k_pd_tv3d_f2s<NN, AN, true, 3>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt, a.theta,
                                      a.dx, a.dy, a.dz, a.zrun, a.gh);
@@ -82,7 +86,8 @@ template <bool NN, bool AN> void lane_entry(int variant, const Args &a) {
 // 4 k_pd_tv3d_f2s with packets two rows ahead, 5 k_pd_tv3d_f2s<PZERO> (dual variable zero on entry, not read),
 // 6 k_pd_tv3d_f2s<L2PF> (prefetches are no-ops on the host: this checks their address arithmetic compiles and the
 //   rest of the kernel is untouched), 7 k_pd_tv3d_f2t (TMA-fed ring of 4 stages), 8 k_pd_tv3d_f2t<GHOST>,
-// 9 k_pd_tv3d_f2t<PZERO> with 2 stages, 10 k_pd_tv3d_f2t with a ring of 8 stages
+// 9 k_pd_tv3d_f2t<PZERO> with 2 stages, 10 k_pd_tv3d_f2t with a ring of 8 stages,
+// 11 k_pd_tv3d_f2s<GHOST, PZERO> (first pair of a sharded prox call: no dual variable read, here or in the ghosts)
 extern "C" int shim_run_fused_tv(int variant, int nonneg, int aniso, const float *in, const float *U, float *Uo,
                                  const float *P1, const float *P2, const float *P3, float *Q1, float *Q2, float *Q3,
                                  float sigma, float tau, float lt, float theta, int dx, int dy, int dz, int zrun,

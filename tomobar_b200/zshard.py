@@ -285,10 +285,11 @@ class ShardedPDTV:
             u_hi = self.slab.ptrs[sh._global(sh.next)] + a * self._ub + plane * 4  # its first own plane
         return u_lo, p_lo, u_hi
 
-    def _ghost_ptrs2(self, a: int):
+    def _ghost_ptrs2(self, a: int, first: bool = False):
         """Peer addresses a fused pass needs from ping-pong set ``a``: the neighbours' last / first TWO
         planes of U, two / one planes of P1..P3 and one plane of the prox input (10 pointers in the
-        argument order of ``tmb_pd_tv_iter2``)."""
+        argument order of ``tmb_pd_tv_iter2``).  ``first``: the first pair of a prox call reads the prox input
+        as its primal variable (the neighbours' inputs as its ghost planes) and no dual variable at all."""
         sh, plane = self.shard, self._plane
         lo = [None] * 5
         hi = [None] * 5
@@ -296,13 +297,19 @@ class ShardedPDTV:
             base = self.slab.ptrs[sh._global(sh.prev)]
             z0p, z1p = shard_bounds(sh.nz_total, sh.world, sh.prev, sh.multiple)
             top = z1p - z0p  # its own planes sit at indices 1 .. top of U and P, 0 .. top - 1 of the input
-            lo = [base + a * self._ub + (top - 1) * plane * 4]
-            lo += [base + 2 * self._ub + (a * 3 + c) * self._pb + (top - 1) * plane * 4 for c in range(3)]
+            if first:
+                lo = [base + self._db + (top - 2) * plane * 4, None, None, None]
+            else:
+                lo = [base + a * self._ub + (top - 1) * plane * 4]
+                lo += [base + 2 * self._ub + (a * 3 + c) * self._pb + (top - 1) * plane * 4 for c in range(3)]
             lo += [base + self._db + (top - 1) * plane * 4]
         if sh.next is not None:
             base = self.slab.ptrs[sh._global(sh.next)]
-            hi = [base + a * self._ub + plane * 4]
-            hi += [base + 2 * self._ub + (a * 3 + c) * self._pb + plane * 4 for c in range(3)]
+            if first:
+                hi = [base + self._db, None, None, None]
+            else:
+                hi = [base + a * self._ub + plane * 4]
+                hi += [base + 2 * self._ub + (a * 3 + c) * self._pb + plane * 4 for c in range(3)]
             hi += [base + self._db]
         return lo + hi
 
@@ -318,17 +325,21 @@ class ShardedPDTV:
         U, P = self.U, self.P
         if self.peer:
             self.sync.acquire()  # nobody still reads the buffers of the previous call
+        ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
+        if self.pairs:
+            self.D.copy_(data)  # the neighbours read planes of the prox input as well
+            if int(iterations) < 2:  # a lone iteration goes through the one-iteration kernel on set 0
+                U[0][1:nzl + 1].copy_(data)
+                for c in range(3):
+                    P[0][c].zero_()
+            self.sync.produced()
+            return self._run_pairs(data, regularisation_parameter, int(iterations), methodTV, nonneg, lipschitz_const,
+                                   ghost_lo, ghost_hi, out)
         U[0][1:nzl + 1].copy_(data)
         for c in range(3):
             P[0][c].zero_()
-        if self.pairs:
-            self.D.copy_(data)  # the neighbours read one plane of the prox input as well
         if self.peer:
             self.sync.produced()
-        ghost_lo, ghost_hi = int(sh.prev is not None), int(sh.next is not None)
-        if self.pairs:
-            return self._run_pairs(data, regularisation_parameter, int(iterations), methodTV, nonneg, lipschitz_const,
-                                   ghost_lo, ghost_hi, out)
         with torch.cuda.device(self.device):
             for it in range(int(iterations)):
                 a, b = it % 2, 1 - it % 2
@@ -360,28 +371,42 @@ class ShardedPDTV:
 
 
     def _run_pairs(self, data, lam, iterations, methodTV, nonneg, lip, ghost_lo, ghost_hi, out):
-        """Pairs of iterations per pass (peer memory): one neighbour synchronisation per launch."""
+        """Pairs of iterations per pass (peer memory): one neighbour synchronisation per launch.  The first pair
+        reads the prox input (in symmetric memory, ``self.D``) as its primal variable and no dual variable --
+        no copy into the primal buffer, no memsets -- and the last launch writes its primal result straight into
+        ``out`` (nobody reads it over NVLink)."""
         from tomobar_b200._lib import lib, check
         from tomobar_b200._tensors import ptr, stream_ptr
 
         nzl, ny, nx = self.shape
         U, P, D = self.U, self.P, self.D
+        if out is None:
+            out = torch.empty_like(data)
+        if iterations <= 0:
+            out.copy_(data)
+            return out
         it, a = 0, 0
         with torch.cuda.device(self.device):
             while it < iterations:
                 b = 1 - a
                 self.sync.acquire()  # the neighbours have finished writing set `a` and reading set `b`
-                if it + 2 <= iterations:
-                    g = self._ghost_ptrs2(a)
-                    check(lib.tmb_pd_tv_iter2(ptr(D), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
-                                              ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
+                pair = it + 2 <= iterations
+                last = it + (2 if pair else 1) >= iterations
+                u_out = ptr(out) if last else ptr(U[b][1:])
+                if pair:
+                    first = it == 0
+                    g = self._ghost_ptrs2(a, first)
+                    u_in = ptr(D) if first else ptr(U[a][1:])
+                    p_in = [None, None, None] if first else [ptr(P[a][c][1:]) for c in range(3)]
+                    check(lib.tmb_pd_tv_iter2(ptr(D), u_in, u_out, p_in[0], p_in[1], p_in[2],
+                                              ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
                                               nzl, ny, nx, float(lam), int(methodTV), int(nonneg), float(lip),
                                               ghost_lo, ghost_hi, *g, stream_ptr(data)), "tmb_pd_tv_iter2")
                     it += 2
                 else:
                     u_lo, p_lo, u_hi = self._ghost_ptrs(a)
                     p_lo = p_lo or [None, None, None]
-                    check(lib.tmb_pd_tv_iter(ptr(D), ptr(U[a][1:]), ptr(U[b][1:]), ptr(P[a][0][1:]), ptr(P[a][1][1:]),
+                    check(lib.tmb_pd_tv_iter(ptr(D), ptr(U[a][1:]), u_out, ptr(P[a][0][1:]), ptr(P[a][1][1:]),
                                              ptr(P[a][2][1:]), ptr(P[b][0][1:]), ptr(P[b][1][1:]), ptr(P[b][2][1:]),
                                              nzl, ny, nx, float(lam), int(methodTV), int(nonneg), float(lip), 0,
                                              ghost_lo, ghost_hi, u_lo, p_lo[0], p_lo[1], p_lo[2], u_hi,
@@ -389,10 +414,6 @@ class ShardedPDTV:
                     it += 1
                 self.sync.produced()
                 a = b
-        res = U[a][1:nzl + 1]
-        if out is None:
-            return res.clone()
-        out.copy_(res)
         return out
 
 
