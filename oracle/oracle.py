@@ -552,11 +552,14 @@ class RecIR:
 
     # methodsIR_CuPy.py:233-309 (with a contiguous first back-projection, i.e. without the
     # swapaxes-view bug of SURVEY.md section 0 item 2)
-    def CGLS(self, data, iterations=30, nonneg=False, mask_radius=1.0):
+    def CGLS(self, data, iterations=30, nonneg=False, mask_radius=1.0, first_bp_data=None):
+        """``first_bp_data``: what the FIRST back-projection reads instead of ``data`` -- the reference hands ASTRA
+        the raw buffer of an axis-swapped view there (methodsIR_CuPy.py:270 with astra_base.py:533-535), and its
+        goldens tests/test_RecToolsIRCuPy.py:152-153, 216-217 encode that."""
         b = self._prep(data)
         shp = self.Atools.vol_shape
         x = np.zeros(int(np.prod(shp)), dtype=np.float32)
-        d = self._Atb(b).ravel()
+        d = self._Atb(b if first_bp_data is None else self._prep(first_bp_data)).ravel()
         normr2 = np.inner(d, d)
         r = b.copy().ravel()
         for _ in range(iterations):

@@ -44,6 +44,12 @@ def load_scan():
 CASES = {
     "landweber_pad1_mean": dict(method="Landweber", pad=1, alg={"iterations": 5}, expect={"mean": 0.0015990591},
                                 atol=1e-3, ref="72-96"),
+    # the two goldens that encode the reference's non-contiguous-view bug: reproduced
+    # with compat_view_bug=True (the first back-projection of CGLS reads the swapped view's raw buffer)
+    "cgls_x15_viewbug": dict(method="CGLS", compat=True, alg={"iterations": 15},
+                             expect={"min": -0.0039929836, "max": 0.024821747}, rtol=1e-4, ref="128-155"),
+    "cgls_x3_after_sirt_viewbug": dict(method="CGLS", compat=True, alg={"iterations": 3},
+                                       expect={"min": -0.0030896277, "max": 0.022553273}, rtol=1e-4, ref="190-218"),
     "cgls_pad50_mask2": dict(method="CGLS", pad=50, alg={"iterations": 15, "recon_mask_radius": 2.0},
                              expect={"min": -0.011976417, "max": 0.0382089}, rtol=1e-4, ref="156-187"),
     "fista_2d_x50": dict(method="FISTA", two_d=True, power=True, alg={"iterations": 50},
@@ -118,6 +124,7 @@ def run_case(case, scan):
     rec = RecToolsIRCuPy(DetectorsDimH=detX, DetectorsDimH_pad=case.get("pad", 0),
                          DetectorsDimV=None if two_d else detY, CenterRotOffset=0.0, AnglesVec=angles,
                          ObjSize=case.get("objsize", detX), device_projector=0, OS_number=case.get("os"))
+    rec.compat_view_bug = bool(case.get("compat", False))
     if two_d:
         _data_ = {"data_fidelity": "LS", "projection_data": data_t[:, 64, :].contiguous(),
                   "data_axes_labels_order": ["angles", "detX"]}

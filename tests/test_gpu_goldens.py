@@ -42,6 +42,17 @@ def test_forwproj_ones(gpu_scan):  # tests/test_RecToolsDIRCuPy.py:669-695
     assert fp.dtype == np.float32 and fp.shape == (128, 180, 160)
 
 
+def test_backproj_view_bug_compat(gpu_scan):  # tests/test_RecToolsDIRCuPy.py:695-717 (the CuPy path's own golden)
+    """The reference back-projects the raw buffer of the swapped view; compat_view_bug=True reproduces its golden."""
+    data, angles = gpu_scan
+    R = _dir(angles, 160, 128)
+    R.compat_view_bug = True
+    bp = R.BACKPROJ(data, data_axes_labels_order=LABELS).cpu().numpy()
+    assert_allclose(bp.max(), 174.80643, rtol=2e-6)
+    assert_allclose(bp.min(), -2.309583, rtol=2e-4)  # the minimum sits on a scrambled edge: 1e-4 from the golden
+    assert bp.shape == (128, 160, 160)
+
+
 def test_backproj(gpu_scan):  # tests/test_RecToolsDIR.py:221-240 (host-array path, correct layout)
     data, angles = gpu_scan
     R = _dir(angles, 160, 128)

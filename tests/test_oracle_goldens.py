@@ -44,6 +44,20 @@ def test_backproj_view_bug_golden(rec):
     assert_allclose(bp.max(), 174.80643, rtol=2e-6)
 
 
+def test_cgls_view_bug_goldens(rec):
+    """tests/test_RecToolsIRCuPy.py:128-155 (CGLS x 15) and :190-218 (CGLS x 3): reproduced only when the first
+    back-projection reads the (180,128,160) buffer as (128,180,160), like the reference does."""
+    O, data, angles, b, ny, nx = rec
+    R = O.RecIR(nx, 0, ny, 0.0, angles, nx)
+    scrambled = np.ascontiguousarray(data).reshape(ny, 180, nx)
+    x = R.CGLS(b, iterations=3, first_bp_data=scrambled)
+    assert_allclose(x.min(), -0.0030896277, rtol=1e-4)
+    assert_allclose(x.max(), 0.022553273, rtol=1e-4)
+    x = R.CGLS(b, iterations=15, first_bp_data=scrambled)
+    assert_allclose(x.min(), -0.0039929836, rtol=1e-4)
+    assert_allclose(x.max(), 0.024821747, rtol=1e-4)
+
+
 def test_fbp3d(rec):
     O, data, angles, b, ny, nx = rec
     R = O.RecDIR(nx, 0, ny, 0.0, angles, nx)

@@ -14,7 +14,7 @@ from tomobar_b200._lib import lib, check
 from tomobar_b200._tensors import as_cuda_f32, ptr, stream_ptr
 from tomobar_b200.fourier import _filtersinc3D_cupy, calc_filter
 from tomobar_b200.projector import ProjTools3D
-from tomobar_b200.supp.funcs import _data_dims_swapper, _parse_device_argument
+from tomobar_b200.supp.funcs import _raw_buffer_view, _data_dims_swapper, _parse_device_argument
 from tomobar_b200.supp.suppTools import _apply_horiz_detector_padding, check_kwargs, edge_pad
 
 
@@ -45,6 +45,8 @@ class RecToolsDIRCuPy:
         quantise_weights: bool = True,
     ):
         self.detectors_x_pad = DetectorsDimH_pad
+        # True: BACKPROJ reproduces the reference's non-contiguous-view behaviour
+        self.compat_view_bug = False
         if CenterRotOffset is None:
             CenterRotOffset = 0.0
         self.centre_of_rotation = CenterRotOffset
@@ -82,6 +84,10 @@ class RecToolsDIRCuPy:
         for key, value in kwargs.items():
             if key == "data_axes_labels_order" and value is not None:
                 data = _data_dims_swapper(data, value, ["detY", "angles", "detX"])
+        if self.compat_view_bug and self.Atools.detectors_x_pad == 0:
+            # bug-for-bug with the reference (its golden tests/test_RecToolsDIRCuPy.py:714-715 encodes it): the
+            # swapped VIEW's raw buffer is back-projected with the view's logical shape
+            data = _raw_buffer_view(data)
         data = _apply_horiz_detector_padding(data, self.Atools.detectors_x_pad, True)
         return self.Atools._backprojCuPy(data)
 

@@ -26,6 +26,7 @@ from tomobar_b200._tensors import as_cuda_f32, ptr, stream_ptr
 from tomobar_b200.projector import ProjTools3D
 from tomobar_b200.regularisersCuPy import PD_TV_cupy, ROF_TV_cupy, prox_regul
 from tomobar_b200.supp.dicts import dicts_check
+from tomobar_b200.supp.funcs import _raw_buffer_view
 from tomobar_b200.supp.suppTools import _apply_horiz_detector_padding, check_kwargs, perform_recon_crop
 
 
@@ -84,6 +85,10 @@ class RecToolsIRCuPy:
         self.data_fidelity = "LS"
         self.nonneg_regul = 0
         self.power_seed = 0  # the reference draws an unseeded cp.random.randn (:326)
+        # True: CGLS's first back-projection reproduces the reference's non-contiguous-view behaviour (:270 with
+        # astra_base.py:533-535) -- the goldens tests/test_RecToolsIRCuPy.py:152-153,
+        # 216-217 encode it
+        self.compat_view_bug = False
         self.zshard = None   # set_zshard(): this object reconstructs one z-block of a larger volume
         self.tv_peer_memory = None  # sharded TV halos: None = NVLink peer loads on NCCL, False = messages
         self.tv_sync = "signals"    # peer-memory ordering: pairwise semaphores, or "barrier"
@@ -195,10 +200,13 @@ class RecToolsIRCuPy:
         uses the logical (contiguous) data; the reference passes a possibly strided view's raw
         pointer there."""
         _data_upd_, _algorithm_upd_, _ = dicts_check(self, _data_, _algorithm_, method_run="CGLS")
+        first = None
+        if self.compat_view_bug and self.Atools.detectors_x_pad == 0:
+            first = _raw_buffer_view(_data_upd_["projection_data"]).contiguous()
         b = self._prepare_data(_data_upd_)
         A = self.Atools
         x_rec = self._zeros_vol()
-        d = A._backprojCuPy(b)
+        d = A._backprojCuPy(b if first is None else first)
         normr2 = self._dot(d, d)
         r = b.clone()
         for _ in range(_algorithm_upd_["iterations"]):

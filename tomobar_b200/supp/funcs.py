@@ -33,6 +33,22 @@ def _data_dims_swapper(data, data_axes_labels_order: Sequence[str], required_lab
     return data.permute(perm)
 
 
+def _raw_buffer_view(data):
+    """What the reference's GPULink hands to ASTRA for a non-contiguous (axis-swapped) view: the raw pointer with
+    the view's LOGICAL shape and a dense pitch (astra_base.py:533-535), i.e. the underlying buffer re-read as if it
+    were contiguous in the new shape.  Only the ``compat_view_bug`` switches use this (SURVEY.md section 0, item 2);
+    the default everywhere is the logically correct array."""
+    if data.is_contiguous():
+        return data
+    import torch
+
+    strides, acc = [], 1
+    for d in reversed(data.shape):
+        strides.append(acc)
+        acc *= int(d)
+    return torch.as_strided(data, tuple(data.shape), tuple(reversed(strides)), data.storage_offset())
+
+
 def _parse_device_argument(device_int_or_string: Union[int, str]) -> Tuple[str, int]:
     """funcs.py:174-187."""
     if isinstance(device_int_or_string, int):
