@@ -96,12 +96,14 @@ int tmb_grad(tmb_geom *g, int subset, int fidelity, const float *x, const float 
  *   ring_rx != NULL : Group-Huber ring model, res += ring_alpha * ring_rx[z][u] (one offset per
  *                     detector pixel), ring_vec[z][u] = sum over the subset's angles of res
  *   huber_delta > 0 : res *= min(1, huber_delta / |res|)
+ *   studentst_sigma > 0 : Student's-t penalty log(1 + res^2 / sigma^2): res = 2 res / (sigma^2 + res^2)
+ *                     (excludes Huber)
  *   weight_mode 1   : PWLS, res *= w          weight_mode 2 : SWLS,
  *                     res = w res - w * (sum_a w res) / (sum_a w + beta_swls)
  * then grad = A_s^T res.  b, w are the full sinograms [nz][na][nu]; ring_rx / ring_vec are [nz][nu]. */
 int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float *b, const float *w, int weight_mode,
-                 float huber_delta, const float *ring_rx, float ring_alpha, float beta_swls, float *ring_vec,
-                 float *grad, void *workspace, void *stream);
+                 float huber_delta, float studentst_sigma, const float *ring_rx, float ring_alpha, float beta_swls,
+                 float *ring_vec, float *grad, void *workspace, void *stream);
 
 /* ---- TV proximal operators ---------------------------------------------------------------
  * tmb_pd_tv  replaces PD_TV_cupy  (regularisersCuPy.py:170-296 + primal_dual_for_total_variation.cu)
@@ -230,6 +232,17 @@ int tmb_fi_pack(const float *tmp_p, float *datac, int n, int nproj, int nz2, voi
 int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
 int tmb_fi_gather(const float *datac, float *fde, const float *theta, const float *sorted_theta,
                   const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream);
+/* The non-default branches of FOURIER_INV (methodsDIR_CuPy.py:759-835, taken for the keyword center_size < 2n):
+ *   tmb_fi_gather_center : tmb_fi_gather restricted to the centre square of center_size x center_size grid points
+ *                          (gather_kernel_center with center_size < 2n, fft_us_kernels.cu:468-527)
+ *   tmb_fi_scatter       : every polar sample spreads its (2m+1)^2 Gaussian footprint onto the grid with atomic adds
+ *                          (gather_kernel :104-109 when center_size == 0: the whole grid, the reference's branch for
+ *                          center_size < 192; gather_kernel_partial :98-102 otherwise: only outside the centre square).
+ *                          fde must be zero where it adds; what is added carries the (-1)^(x+y) like tmb_fi_gather.   */
+int tmb_fi_gather_center(const float *datac, float *fde, const float *theta, const float *sorted_theta,
+                         const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, int center_size, void *stream);
+int tmb_fi_scatter(const float *datac, float *fde, const float *theta, int m, float mu, int center_size, int n,
+                   int nproj, int nz2, void *stream);
 int tmb_fi_sign2d(float *fde, int n, int nz2, void *stream);
 int tmb_fi_unpad(float *recon, const float *fde, float mu, int nproj, int unpad_recon_p, int unpad_z,
                  int unpad_recon_m, int n, int nz2, void *stream);

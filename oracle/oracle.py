@@ -606,7 +606,7 @@ class RecIR:
     # Extension (no code in this reference snapshot; legacy call sites
     # Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:197,243,307-309): residual of the Huber /
     # Group-Huber ring / SWLS data terms.  Defines the semantics the CUDA path (k_resid_post) is held to.
-    def residual_ext(self, x, b, use_os, sub_ind, indVec, w, fidelity, huber, r_x, alpha, beta):
+    def residual_ext(self, x, b, use_os, sub_ind, indVec, w, fidelity, huber, r_x, alpha, beta, studentst=None):
         res = (self._Ax(x, sub_ind, use_os) - b).astype(np.float32)
         vec = None
         if r_x is not None:
@@ -618,6 +618,8 @@ class RecIR:
             absr = np.abs(res)
             with np.errstate(divide="ignore", invalid="ignore"):
                 res = np.where(absr > f32(huber), res * (f32(huber) / absr), res).astype(np.float32)
+        if studentst is not None:  # Student's-t penalty log(1 + r^2 / sigma^2): gradient 2 r / (sigma^2 + r^2)
+            res = ((f32(2.0) * res) / (f32(f32(studentst) * f32(studentst)) + res * res)).astype(np.float32)
         if fidelity in ("PWLS", "SWLS"):
             ws = w[:, indVec, :] if use_os else w
             res = res * ws
@@ -633,10 +635,11 @@ class RecIR:
     # methodsIR_CuPy.py:401-484
     def FISTA(self, data, iterations, lipschitz_const=None, regularisation=None, nonneg=False,
               fidelity="LS", initialise=None, mask_radius=1.0, huber_threshold=None, ringGH_lambda=None,
-              ringGH_accelerate=50, beta_SWLS=0.1):
+              ringGH_accelerate=50, beta_SWLS=0.1, studentst_threshold=None):
         reg = _reg_defaults(regularisation)
         b_all, L, x0, w = self._init(data, "PWLS" if fidelity == "SWLS" else fidelity, initialise, lipschitz_const)
-        extended = huber_threshold is not None or ringGH_lambda is not None or fidelity == "SWLS"
+        extended = (huber_threshold is not None or ringGH_lambda is not None or fidelity == "SWLS"
+                    or studentst_threshold is not None)
         r = r_x = None
         if ringGH_lambda is not None:
             r = np.zeros((b_all.shape[0], b_all.shape[2]), np.float32)
@@ -657,7 +660,7 @@ class RecIR:
                     b = b_all[:, indVec, :]
                 if extended:
                     res, vec = self.residual_ext(X_t, b, use_os, sub, indVec, w, fidelity, huber_threshold, r_x,
-                                                 ringGH_accelerate, beta_SWLS)
+                                                 ringGH_accelerate, beta_SWLS, studentst_threshold)
                     grad = self._Atb(res, sub, use_os)
                     if r is not None:
                         r_old = r

@@ -144,7 +144,7 @@ def ref_filtersinc(n, cutoff, multiplier, device="cuda"):
 
 
 def ref_FOURIER_INV(data, angles, recon_size, cor=0.0, pad=0, filter_type="shepp", cutoff_freq=1.0,
-                    use_naive_prune=False):
+                    use_naive_prune=False, center_size=32768):
     """Default path of RecToolsDIRCuPy.FOURIER_INV (methodsDIR_CuPy.py:152-447) with the
     reference's own fft_us_kernels.cu kernels and launch geometry; data [detY, angles, detX]."""
     import math
@@ -162,13 +162,13 @@ def ref_FOURIER_INV(data, angles, recon_size, cor=0.0, pad=0, filter_type="shepp
         dp[: nz - odd_v, :, -int(odd_h)] = data[..., -int(odd_h)]
         data = dp
     n = data_n + 2 * pad
-    center_size = min(32768, 2 * n)
+    center_size = min(center_size, 2 * n)
     theta = torch.as_tensor(-np.asarray(angles), dtype=torch.float32, device=dev)
     sidx = torch.argsort(theta)
     sth = theta[sidx].contiguous()
     sth_cpu = sth.cpu().numpy()
     pi_count = 1 + int(np.ceil(abs(sth_cpu[nproj - 1] - sth_cpu[0]) / math.pi))
-    angle_range = torch.zeros((center_size, center_size, 1 + pi_count * 2), dtype=torch.int16, device=dev)
+    angle_range = torch.zeros((max(center_size, 1), max(center_size, 1), 1 + pi_count * 2), dtype=torch.int16, device=dev)
     eps = 1e-4
     mu = -np.log(eps) / (2 * n * n)
     # filtering (:449-545)
@@ -187,7 +187,8 @@ def ref_FOURIER_INV(data, angles, recon_size, cor=0.0, pad=0, filter_type="shepp
         tmp_p[z] = tmp[0, :, unpad_m:unpad_p]
     nz2 = nz // 2
     datac = torch.empty((nz2, nproj, n), dtype=torch.complex64, device=dev)
-    fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+    # (zeros: the scatter branches add into it, methodsDIR_CuPy.py:661-670)
+    fde = torch.zeros((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
     i32 = np.int32
     cdiv = lambda a, b: int(np.ceil(a / b))
     mod.launch("r2c_c1dfftshift", (cdiv(n, 32), cdiv(nproj, 32), nz2), (32, 32, 1), [tmp_p, datac, i32(n), i32(nproj), i32(nz2)])
@@ -195,12 +196,19 @@ def ref_FOURIER_INV(data, angles, recon_size, cor=0.0, pad=0, filter_type="shepp
     m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
     mod.launch("c1dfftshift", (cdiv(n, 32), cdiv(nproj, 32), nz2), (32, 32, 1),
                [datac, np.float32(4 / n), i32(n), i32(nproj), i32(nz2)])
-    prune = "gather_kernel_center_prune_naive" if use_naive_prune else "gather_kernel_center_angle_based_prune"
-    mod.launch(prune, (cdiv(center_size, 256), center_size, 1), (256, 1, 1),
-               [angle_range, i32(pi_count * 2 + 1), sth, i32(m), i32(center_size), i32(n), i32(nproj)])
-    mod.launch("gather_kernel_center", (cdiv(center_size, 32), cdiv(center_size, 4), nz2), (32, 4, 1),
-               [datac, fde, angle_range, i32(pi_count * 2 + 1), theta, sidx.to(torch.int64).contiguous(), i32(m),
-                np.float32(mu), i32(center_size), i32(n), i32(nproj), i32(nz2)])
+    if center_size >= 192:  # _CENTER_SIZE_MIN (methodsDIR_CuPy.py:23, 759-816)
+        if center_size != 2 * n:
+            mod.launch("gather_kernel_partial", (cdiv(n, 16), cdiv(nproj, 16), nz2), (16, 16, 1),
+                       [datac, fde, theta, i32(m), np.float32(mu), i32(center_size), i32(n), i32(nproj), i32(nz2)])
+        prune = "gather_kernel_center_prune_naive" if use_naive_prune else "gather_kernel_center_angle_based_prune"
+        mod.launch(prune, (cdiv(center_size, 256), center_size, 1), (256, 1, 1),
+                   [angle_range, i32(pi_count * 2 + 1), sth, i32(m), i32(center_size), i32(n), i32(nproj)])
+        mod.launch("gather_kernel_center", (cdiv(center_size, 32), cdiv(center_size, 4), nz2), (32, 4, 1),
+                   [datac, fde, angle_range, i32(pi_count * 2 + 1), theta, sidx.to(torch.int64).contiguous(), i32(m),
+                    np.float32(mu), i32(center_size), i32(n), i32(nproj), i32(nz2)])
+    else:  # :818-835
+        mod.launch("gather_kernel", (cdiv(n, 16), cdiv(nproj, 16), nz2), (16, 16, 1),
+                   [datac, fde, theta, i32(m), np.float32(mu), i32(n), i32(nproj), i32(nz2)])
     mod.launch("c2dfftshift", (cdiv(2 * n, 32), cdiv(2 * n, 8), nz2), (32, 8, 1), [fde, i32(n), i32(nz2)])
     for z in range(nz2):
         fde[z] = torch.fft.ifft2(fde[z])

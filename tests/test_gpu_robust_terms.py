@@ -1,4 +1,4 @@
-"""Huber / Group-Huber ring / SWLS data terms (extension; the reference snapshot keeps only their
+"""Huber / Student's-t / Group-Huber ring / SWLS data terms (extension; the reference snapshot keeps only their
 legacy call sites, so parity is pinned to the oracle's definition, oracle/oracle.py residual_ext):
 CUDA path vs oracle on a synthetic sinogram with outliers and stripes."""
 
@@ -21,7 +21,7 @@ def _problem(seed=0, nz=6, n=48, na=60):
 
 
 @pytest.mark.parametrize("os_n", [None, 4])
-@pytest.mark.parametrize("case", ["huber", "ring", "huber+ring+pwls", "swls"])
+@pytest.mark.parametrize("case", ["huber", "ring", "huber+ring+pwls", "swls", "studentst", "studentst+ring"])
 def test_fista_robust_terms_match_oracle(oracle, os_n, case):
     from tomobar_b200.methodsIR_CuPy import RecToolsIRCuPy
 
@@ -36,6 +36,8 @@ def test_fista_robust_terms_match_oracle(oracle, os_n, case):
     kw, data = {}, {"projection_data": torch.from_numpy(b).cuda()}
     if "huber" in case:
         kw["huber_threshold"] = 0.5
+    if "studentst" in case:
+        kw["studentst_threshold"] = 0.7
     if "ring" in case:
         kw.update(ringGH_lambda=2e-3, ringGH_accelerate=8)
     fid = "PWLS" if "pwls" in case else ("SWLS" if case == "swls" else "LS")

@@ -37,7 +37,7 @@ SIGNATURES = {
     "tmb_fp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_bp3d": (_i, [_vp, _i, _fp, _fp, _vp, _vp]),
     "tmb_grad": (_i, [_vp, _i, _i, _fp, _fp, _fp, _fp, _vp, _vp]),
-    "tmb_grad_ext": (_i, [_vp, _i, _fp, _fp, _fp, _i, _f, _fp, _f, _f, _fp, _fp, _vp, _vp]),
+    "tmb_grad_ext": (_i, [_vp, _i, _fp, _fp, _fp, _i, _f, _f, _fp, _f, _f, _fp, _fp, _vp, _vp]),
     "tmb_tv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tmb_pd_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _i, _i, _f, _i, _vp, _vp]),
     "tmb_rof_tv": (_i, [_fp, _fp, _i, _i, _i, _f, _i, _f, _i, _vp, _vp]),
@@ -61,6 +61,8 @@ SIGNATURES = {
     "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),
     "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
     "tmb_fi_gather": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _vp]),
+    "tmb_fi_gather_center": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
+    "tmb_fi_scatter": (_i, [_fp, _fp, _fp, _i, _f, _i, _i, _i, _i, _vp]),
     "tmb_fi_sign2d": (_i, [_fp, _i, _i, _vp]),
     "tmb_fi_unpad": (_i, [_fp, _fp, _f, _i, _i, _i, _i, _i, _i, _vp]),
     "tmb_fp3d_host": (_i, [_vp, _i, _fp, _fp]),

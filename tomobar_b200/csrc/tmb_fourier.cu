@@ -132,12 +132,14 @@ __device__ __forceinline__ void fi_line(const float2 *__restrict__ g, float thet
 __global__ void __launch_bounds__(128)
     k_fi_gather(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta,
                 const float *__restrict__ sth, const int *__restrict__ sidx, int m, float mu, int n, int nproj,
-                int nz2) {
+                int nz2, int center_size) {
   const int n2 = 2 * n;
-  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+  // the centre square of the grid (gather_kernel_center, :468-527): center_size == 2n is the whole grid
+  const int c0 = max(0, n - center_size / 2);
+  const int lx = blockIdx.x * blockDim.x + threadIdx.x, ly = blockIdx.y * blockDim.y + threadIdx.y;
+  const int tx = c0 + lx, ty = c0 + ly;
   const int z0 = blockIdx.z * FI_SC;
-  if (tx >= n2 || ty >= n2) return;
+  if (lx >= center_size || ly >= center_size || tx >= n2 || ty >= n2) return;
   const int nzc = min(FI_SC, nz2 - z0);
   const float coeff0 = FI_PI / mu;
   const float coeff1 = -FI_PI * FI_PI / mu;
@@ -185,6 +187,59 @@ __global__ void __launch_bounds__(128)
     if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = make_float2(acc[s].x * sg, acc[s].y * sg);
 }
 
+// The scatter ("gather_kernel" / "gather_kernel_partial", fft_us_kernels.cu:44-109) of the non-default branches
+// (methodsDIR_CuPy.py:761-779, 818-835: center_size < 192, or a centre square smaller than the grid): every polar
+// sample spreads its (2m+1)^2 Gaussian footprint onto the grid with atomic adds; PARTIAL skips the targets inside
+// the centre square, which the centre gather fills.  One thread owns one sample of FI_SC complex slices (one weight
+// evaluation serves the chunk); the (-1)^(x+y) of the centred inverse 2-D FFT is applied to what is added, as in
+// k_fi_gather's store.  The grid must be zero on entry where the scatter adds.
+template <bool PARTIAL>
+__global__ void __launch_bounds__(256)
+    k_fi_scatter(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta, int m, float mu,
+                 int center_size, int n, int nproj, int nz2) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+  const int z0 = blockIdx.z * FI_SC;
+  if (tx >= n || ty >= nproj) return;
+  const int nzc = min(FI_SC, nz2 - z0);
+  const int ch = center_size / 2;
+  const float coeff0 = FI_PI / mu;
+  const float coeff1 = -FI_PI * FI_PI / mu;
+  float st, ct;
+  __sincosf(__ldg(theta + ty), &st, &ct);
+  float x0 = (tx - n / 2) / (float)n * ct;
+  float y0 = -(tx - n / 2) / (float)n * st;
+  if (x0 >= 0.5f) x0 = 0.5f - 1e-5;
+  if (y0 >= 0.5f) y0 = 0.5f - 1e-5;
+  const int n2 = 2 * n;
+  const size_t fs2 = (size_t)n2 * n2, plane = (size_t)n * nproj;
+  float2 g0[FI_SC];
+#pragma unroll
+  for (int s = 0; s < FI_SC; ++s)
+    g0[s] = s < nzc ? __ldg(g + (size_t)(z0 + s) * plane + (size_t)ty * n + tx) : make_float2(0.f, 0.f);
+  const int bx = (int)floorf(2 * n * x0) - m, by = (int)floorf(2 * n * y0) - m;
+  for (int i1 = 0; i1 < 2 * m + 1; ++i1) {
+    const int ell1 = by + i1;
+    for (int i0 = 0; i0 < 2 * m + 1; ++i0) {
+      const int ell0 = bx + i0;
+      if (PARTIAL && !(ell0 < -ch || ell0 >= ch || ell1 < -ch || ell1 >= ch)) continue;
+      const float w0 = ell0 / (float)(2 * n) - x0, w1 = ell1 / (float)(2 * n) - y0;
+      float w = coeff0 * __expf(coeff1 * (w0 * w0 + w1 * w1));
+      // target (column, row) of the 2n x 2n grid: the reference offsets f by (n, n) and wraps (:20, :40)
+      const int col = (ell0 + 3 * n) % n2, row = (ell1 + 3 * n) % n2;
+      if ((col ^ row) & 1) w = -w;
+      float2 *dst = f + (size_t)z0 * fs2 + (size_t)row * n2 + col;
+#pragma unroll
+      for (int s = 0; s < FI_SC; ++s) {
+        if (s < nzc) {
+          atomicAdd(&dst[(size_t)s * fs2].x, w * g0[s].x);
+          atomicAdd(&dst[(size_t)s * fs2].y, w * g0[s].y);
+        }
+      }
+    }
+  }
+}
+
 __global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__ f, float mu, int nproj, int up,
                            int unpad_z, int um, int n, int nz2) {
   const int rxu = blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,15 +283,47 @@ extern "C" int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz
   return check_launch("k_fi_scale_sign");
 }
 
+static int fi_gather_launch(const float *datac, float *fde, const float *theta, const float *sorted_theta,
+                            const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, int center_size,
+                            void *stream) {
+  dim3 block(32, 4), grid((center_size + 31) / 32, (center_size + 3) / 4, (nz2 + FI_SC - 1) / FI_SC);
+  k_fi_gather<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
+                                                        reinterpret_cast<float2 *>(fde), theta, sorted_theta,
+                                                        sorted_idx, m, mu, n, nproj, nz2, center_size);
+  return check_launch("k_fi_gather");
+}
+
 extern "C" int tmb_fi_gather(const float *datac, float *fde, const float *theta, const float *sorted_theta,
                              const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream) {
   TMB_REQUIRE(datac && fde && theta && sorted_theta && sorted_idx, "tmb_fi_gather: null argument");
   TMB_REQUIRE(n > 0 && nproj > 0 && nz2 > 0 && m > 0 && mu > 0.f, "tmb_fi_gather: bad argument");
-  dim3 block(32, 4), grid((2 * n + 31) / 32, (2 * n + 3) / 4, (nz2 + FI_SC - 1) / FI_SC);
-  k_fi_gather<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
-                                                        reinterpret_cast<float2 *>(fde), theta, sorted_theta,
-                                                        sorted_idx, m, mu, n, nproj, nz2);
-  return check_launch("k_fi_gather");
+  return fi_gather_launch(datac, fde, theta, sorted_theta, sorted_idx, m, mu, n, nproj, nz2, 2 * n, stream);
+}
+
+extern "C" int tmb_fi_gather_center(const float *datac, float *fde, const float *theta, const float *sorted_theta,
+                                    const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, int center_size,
+                                    void *stream) {
+  TMB_REQUIRE(datac && fde && theta && sorted_theta && sorted_idx, "tmb_fi_gather_center: null argument");
+  TMB_REQUIRE(n > 0 && nproj > 0 && nz2 > 0 && m > 0 && mu > 0.f, "tmb_fi_gather_center: bad argument");
+  TMB_REQUIRE(center_size > 0 && center_size <= 2 * n && center_size % 2 == 0, "tmb_fi_gather_center: bad centre size");
+  return fi_gather_launch(datac, fde, theta, sorted_theta, sorted_idx, m, mu, n, nproj, nz2, center_size, stream);
+}
+
+extern "C" int tmb_fi_scatter(const float *datac, float *fde, const float *theta, int m, float mu, int center_size,
+                              int n, int nproj, int nz2, void *stream) {
+  TMB_REQUIRE(datac && fde && theta, "tmb_fi_scatter: null argument");
+  TMB_REQUIRE(n > 0 && nproj > 0 && nz2 > 0 && m > 0 && mu > 0.f && center_size >= 0 && center_size <= 2 * n,
+              "tmb_fi_scatter: bad argument");
+  dim3 block(16, 16), grid((n + 15) / 16, (nproj + 15) / 16, (nz2 + FI_SC - 1) / FI_SC);
+  if (center_size > 0)
+    k_fi_scatter<true><<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
+                                                                  reinterpret_cast<float2 *>(fde), theta, m, mu,
+                                                                  center_size, n, nproj, nz2);
+  else
+    k_fi_scatter<false><<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
+                                                                   reinterpret_cast<float2 *>(fde), theta, m, mu, 0, n,
+                                                                   nproj, nz2);
+  return check_launch("k_fi_scatter");
 }
 
 extern "C" int tmb_fi_sign2d(float *fde, int n, int nz2, void *stream) {

@@ -626,6 +626,7 @@ struct PostArgs {
   int nz, nu, up, na_loc, na_tot, g_first, g_stride;
   int weight_mode;     // 0 none, 1 PWLS, 2 SWLS
   float alpha, delta, beta;
+  float sigma2;        // Student's-t scale squared (0: off)
 };
 
 __device__ __forceinline__ float huber_w(float r, float delta) {
@@ -659,6 +660,7 @@ __global__ void k_resid_post(const PostArgs p) {
         vec[q] = __fadd_rn(vec[q], v);
       }
       if (p.delta > 0.f) v = huber_w(v, p.delta);
+      if (p.sigma2 > 0.f) v = __fdiv_rn(__fmul_rn(2.f, v), __fadd_rn(p.sigma2, __fmul_rn(v, v)));  // Student's t
       if (p.weight_mode) {
         const float wv = p.w[((size_t)(zc * ZC + q) * p.na_tot + ga) * p.nu + u];
         v = __fmul_rn(v, wv);
@@ -877,13 +879,15 @@ extern "C" int tmb_grad(tmb_geom *g, int subset, int fidelity, const float *x, c
 
 // Gradient of the robust / ring-artefact data terms (extension of tmb_grad; see k_resid_post).
 extern "C" int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float *b, const float *w,
-                            int weight_mode, float huber_delta, const float *ring_rx, float ring_alpha,
-                            float beta_swls, float *ring_vec, float *grad, void *workspace, void *stream) {
+                            int weight_mode, float huber_delta, float studentst_sigma, const float *ring_rx,
+                            float ring_alpha, float beta_swls, float *ring_vec, float *grad, void *workspace,
+                            void *stream) {
   TMB_REQUIRE(g && x && b && grad && workspace, "tmb_grad_ext: null argument");
   TMB_REQUIRE(subset >= -1 && subset < g->os_number, "tmb_grad_ext: subset out of range");
   TMB_REQUIRE(weight_mode >= 0 && weight_mode <= 2, "tmb_grad_ext: weight_mode must be 0 (none), 1 (PWLS), 2 (SWLS)");
   TMB_REQUIRE(weight_mode == 0 || w, "tmb_grad_ext: weights missing");
   TMB_REQUIRE(!ring_rx == !ring_vec, "tmb_grad_ext: ring_rx and ring_vec go together");
+  TMB_REQUIRE(!(huber_delta > 0.f && studentst_sigma > 0.f), "tmb_grad_ext: Huber and Student's-t exclude each other");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Ws ws = carve(g, workspace);
   int rc = launch_vol_to_int(g, x, ws.v0, ws.v1, st);
@@ -896,6 +900,7 @@ extern "C" int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float
   a.nz = g->d.nz; a.nu = g->d.nu; a.up = g->d.up; a.na_loc = subset_size(g, subset); a.na_tot = g->d.na;
   a.g_first = subset < 0 ? 0 : subset; a.g_stride = subset < 0 ? 1 : g->os_number;
   a.weight_mode = weight_mode; a.alpha = ring_alpha; a.delta = huber_delta; a.beta = beta_swls;
+  a.sigma2 = studentst_sigma > 0.f ? studentst_sigma * studentst_sigma : 0.f;
   dim3 grid((g->d.nu + 127) / 128, (g->d.nz + ZC - 1) / ZC);
   k_resid_post<<<grid, 128, 0, st>>>(a);
   rc = check_launch("k_resid_post");

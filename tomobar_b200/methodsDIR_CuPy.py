@@ -110,6 +110,7 @@ class RecToolsDIRCuPy:
 
     # ------------------------------------------------------------------------------------------
     _FILTERS = ("none", "ramp", "shepp", "cosine", "cosine2", "hamming", "hann", "parzen")
+    _CENTER_SIZE_MIN = 192  # methodsDIR_CuPy.py:23
 
     def FOURIER_INV(self, data, **kwargs) -> torch.Tensor:
         """Direct Fourier inversion on unequally spaced grids (USFFT gridding, Nikitin's
@@ -122,9 +123,10 @@ class RecToolsDIRCuPy:
             cutoff_freq (float): filter cutoff (default 1.0).
             padding (int): extra zero padding of the frequency grid.
             power_of_2_oversampling / power_of_2_cropping (bool): as in the reference.
+            center_size (int): side of the centre square of the frequency grid that is gathered; the rest is
+                scattered with atomic adds, everything when it is below 192 (default: the whole grid is gathered).
         The memory-tuning keywords of the reference (chunk_count, min_mem_usage_*, block_dim*) are
-        accepted and ignored; ``center_size`` smaller than the full grid (the scatter kernels) is
-        not built.
+        accepted and ignored.
         """
         if isinstance(data, tuple):
             # dry run under an active DeviceMemStack: record this implementation's allocations
@@ -137,6 +139,7 @@ class RecToolsDIRCuPy:
         power_of_2_oversampling = True
         power_of_2_cropping = False
         padding = 0
+        center_size = 32768
         data = as_cuda_f32(data, self.Atools.device, "projection data")
         for key, value in kwargs.items():
             if value is None:
@@ -144,8 +147,7 @@ class RecToolsDIRCuPy:
             if key == "data_axes_labels_order":
                 data = _data_dims_swapper(data, value, ["detY", "angles", "detX"])
             elif key == "center_size":
-                if value < 2 * (data.shape[-1] + 2 * self.detectors_x_pad):
-                    raise NotImplementedError("FOURIER_INV: only the full-grid centre gather is built")
+                center_size = int(value)
             elif key == "cutoff_freq":
                 cutoff_freq = value
             elif key == "filter_type":
@@ -212,11 +214,26 @@ class RecToolsDIRCuPy:
             datac = torch.fft.fft(datac, dim=-1)
             check(lib.tmb_fi_scale_sign(ptr(datac), float(np.float32(4 / n)), n, nproj, nz2, st), "tmb_fi_scale_sign")
             m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
-            # STEP 2: gather polar samples onto the 2n x 2n Cartesian grid (:781-816); the (-1)^(x+y)
-            # before the 2-D FFT is applied by the gather, the one after it by the unpadding kernel
-            fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
-            check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
-                                    float(np.float32(mu)), n, nproj, nz2, st), "tmb_fi_gather")
+            # STEP 2: polar samples onto the 2n x 2n Cartesian grid (:756-835); the (-1)^(x+y) before the 2-D
+            # FFT is applied by these kernels, the one after it by the unpadding kernel.  Three branches, chosen
+            # by the centre size like the reference: the whole grid gathered (default), a centre square gathered
+            # and the rest scattered with atomic adds, or everything scattered (centre below _CENTER_SIZE_MIN)
+            center_size = min(center_size, 2 * n)
+            center_size -= center_size % 2
+            if center_size >= self._CENTER_SIZE_MIN and center_size == 2 * n:
+                fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+                check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
+                                        float(np.float32(mu)), n, nproj, nz2, st), "tmb_fi_gather")
+            else:
+                # (the reference adds onto cp.empty memory in the partial branch, :661-670; zeros are what it means)
+                fde = torch.zeros((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+                partial = center_size >= self._CENTER_SIZE_MIN
+                check(lib.tmb_fi_scatter(ptr(datac), ptr(fde), ptr(theta), m, float(np.float32(mu)),
+                                         center_size if partial else 0, n, nproj, nz2, st), "tmb_fi_scatter")
+                if partial:
+                    check(lib.tmb_fi_gather_center(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta),
+                                                   ptr(sorted_idx), m, float(np.float32(mu)), n, nproj, nz2,
+                                                   center_size, st), "tmb_fi_gather_center")
             del datac
             # STEP 3: centred 2-D inverse FFT (:851-896)
             chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))  # bound cuFFT workspace

@@ -342,8 +342,11 @@ class RecToolsIRCuPy:
         # Group-Huber ring model (one offset r per detector pixel, soft-thresholded, with its own
         # momentum) and stripe-weighted least squares
         huber = _data_upd_.get("huber_threshold")
+        studentst = _data_upd_.get("studentst_threshold")
         ring_lambda = _data_upd_.get("ringGH_lambda")
-        extended = huber is not None or ring_lambda is not None or self.data_fidelity == "SWLS"
+        extended = huber is not None or studentst is not None or ring_lambda is not None or self.data_fidelity == "SWLS"
+        if huber is not None and studentst is not None:
+            raise ValueError("huber_threshold and studentst_threshold exclude each other")
         if extended and self.data_fidelity == "KL":
             raise ValueError("Huber / ring / SWLS models combine with the LS and PWLS data terms only")
         r = r_x = vec = None
@@ -359,7 +362,7 @@ class RecToolsIRCuPy:
                     if extended:
                         A.grad_data_term_ext(X_t, b, sub_ind if use_os else None, self.data_fidelity, w, huber,
                                              r_x, float(_data_upd_["ringGH_accelerate"]),
-                                             float(_data_upd_["beta_SWLS"]), vec, out=G)
+                                             float(_data_upd_["beta_SWLS"]), vec, out=G, studentst_threshold=studentst)
                         if r is not None:
                             r_old = r
                             r = r_x - np.float32(L_const_inv) * vec

@@ -214,8 +214,9 @@ class ProjTools3D:
                            fidelity: str = "LS", w_full: Optional[torch.Tensor] = None,
                            huber_threshold: Optional[float] = None, ring_rx: Optional[torch.Tensor] = None,
                            ring_alpha: float = 0.0, beta_swls: float = 0.0,
-                           ring_vec: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """grad = A_s^T rho'(A_s x - b_s) for the Huber / Group-Huber ring / SWLS models; ``ring_vec``
+                           ring_vec: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                           studentst_threshold: Optional[float] = None) -> torch.Tensor:
+        """grad = A_s^T rho'(A_s x - b_s) for the Huber / Student's-t / Group-Huber ring / SWLS models; ``ring_vec``
         ([nz, nu]) receives the angle-sum of the ring-corrected residual."""
         sub = self._sub(os_index)
         mode = {"LS": 0, "PWLS": 1, "SWLS": 2}[fidelity]
@@ -230,7 +231,8 @@ class ProjTools3D:
             out = torch.empty(self.vol_geom, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(lib.tmb_grad_ext(self._g, sub, ptr(x), ptr(b_full), ptr(w_full) if mode else None, mode,
-                                   float(huber_threshold or 0.0), ptr(ring_rx) if ring_rx is not None else None,
+                                   float(huber_threshold or 0.0), float(studentst_threshold or 0.0),
+                                   ptr(ring_rx) if ring_rx is not None else None,
                                    float(ring_alpha), float(beta_swls),
                                    ptr(ring_vec) if ring_rx is not None else None, ptr(out),
                                    ptr(self._workspace()), stream_ptr(out)), "tmb_grad_ext")

@@ -83,6 +83,7 @@ def dicts_check(
     # robust / ring-artefact extensions: absent from this reference snapshot's dicts.py, keys and
     # defaults as in its legacy demos (Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:197,243,307-309)
     _data_.setdefault("huber_threshold", None)
+    _data_.setdefault("studentst_threshold", None)
     _data_.setdefault("ringGH_lambda", None)
     _data_.setdefault("ringGH_accelerate", 50)
     _data_.setdefault("beta_SWLS", 0.1)
