@@ -1,0 +1,85 @@
+"""tmb_fp3d_host / tmb_bp3d_host (include/tmb.h: host pointers in, host pointers out -- the calls a caller without
+device arrays binds) against the oracle and against the device-pointer entry points; and a single
+process that reconstructs on cuda:0 and then on cuda:1 (the shared-memory attribute of the kernels is per device)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nz,n,nu,na,os_n", [(5, 48, 64, 30, None), (33, 70, 70, 40, 4)])
+def test_host_entry_points_vs_oracle(oracle, nz, n, nu, na, os_n):
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200.projector import ProjTools3D
+
+    rng = np.random.default_rng(nz)
+    angles = np.linspace(0, np.pi, na, endpoint=False).astype(np.float32)
+    P = ProjTools3D(nu, 0, nz, angles, 0.25, n, "gpu", 0, os_n)
+    O = oracle.Atools(nu, 0, nz, angles, 0.25, n, os_n)
+    fp = C.c_void_p  # plain host addresses
+    vol = rng.standard_normal((nz, n, n)).astype(np.float32)
+    for sub in ([-1] if os_n is None else [0, os_n - 1]):
+        na_s = na if sub < 0 else len(O.tbl_os[sub])
+        sino = np.empty((nz, na_s, nu), np.float32)
+        check(lib.tmb_fp3d_host(P._g, sub, vol.ctypes.data_as(fp), sino.ctypes.data_as(fp)), "tmb_fp3d_host")
+        want = O._forwprojCuPy(vol) if sub < 0 else O._forwprojOSCuPy(vol, sub)
+        assert rel_max(sino, want) < 2e-6
+        dev = P._forwprojCuPy(torch.from_numpy(vol).cuda()) if sub < 0 else P._forwprojOSCuPy(torch.from_numpy(vol).cuda(), sub)
+        assert np.array_equal(sino, dev.cpu().numpy())  # same kernels behind both entry points
+        back = np.empty((nz, n, n), np.float32)
+        check(lib.tmb_bp3d_host(P._g, sub, want.ctypes.data_as(fp), back.ctypes.data_as(fp)), "tmb_bp3d_host")
+        want_b = O._backprojCuPy(want) if sub < 0 else O._backprojOSCuPy(want, sub)
+        assert rel_max(back, want_b) < 2e-6
+
+
+def test_one_process_two_devices(oracle):
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device; it used to be set once per process,
+    so the second device of a process failed every FP / TV launch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tomobar_b200.methodsIR_CuPy import RecToolsIRCuPy
+
+    nz, n, na = 20, 64, 48
+    angles = np.linspace(0, np.pi, na, endpoint=False).astype(np.float32)
+    rng = np.random.default_rng(0)
+    b = rng.random((nz, na, n)).astype(np.float32)
+    res = []
+    for d in (0, 1):
+        rec = RecToolsIRCuPy(n, 0, nz, 0.0, angles, n, d, 4)
+        x = rec.FISTA({"projection_data": torch.from_numpy(b).to(f"cuda:{d}")},
+                      {"iterations": 2, "lipschitz_const": 3000.0, "nonnegativity": True},
+                      {"method": "PD_TV", "regul_param": 1e-3, "iterations": 6})
+        assert x.device.index == d
+        res.append(x.cpu().numpy())
+    assert np.array_equal(res[0], res[1])
+
+
+def test_two_geometries_on_two_streams(oracle):
+    """the per-angle constants of ALL geometries share one __constant__ table per device.  Two geometries
+    used alternately on two streams must not overwrite the table under each other's kernels (uploads wait, on the
+    device, for the streams still reading the resident table)."""
+    from tomobar_b200.projector import ProjTools3D
+
+    nz, n = 24, 96
+    geoms = [ProjTools3D(n, 0, nz, np.linspace(0, np.pi, na, endpoint=False).astype(np.float32), cor, n, "gpu", 0, None)
+             for na, cor in ((90, 0.0), (75, 1.5))]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    vols = [torch.rand((nz, n, n), device="cuda", generator=g) for _ in geoms]
+    want = [G._backprojCuPy(G._forwprojCuPy(v)).clone() for G, v in zip(geoms, vols)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [[], []]
+    for _ in range(6):
+        for i, (G, v, s) in enumerate(zip(geoms, vols, streams)):
+            with torch.cuda.stream(s):
+                got[i].append(G._backprojCuPy(G._forwprojCuPy(v)))
+    torch.cuda.synchronize()
+    for i in range(2):
+        for r in got[i]:
+            assert torch.equal(r, want[i])

@@ -122,11 +122,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// try_wait suspends the thread for a hardware time slice per attempt; a barrier that has not
-// completed after ~4 M attempts means a lost copy (bad size / alignment): trap instead of hanging
+// try_wait suspends the thread for a hardware time slice per attempt.  A barrier that has not completed after
+// 30 SECONDS of wall clock (%globaltimer, looked at every 4096 attempts) means a lost copy (bad size / alignment):
+// trap instead of hanging the device.  The bound is a time, not an attempt count, so that time-slicing, MPS, a
+// debugger or a profiler replay stretching a healthy copy cannot trip it.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-    if (spins > (1u << 22)) __trap();
+  uint64_t t0 = 0;
+  for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+    if ((spins & 0xfffu) == 0) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 30000000000ull) __trap();
+    }
+  }
 }
 // plain spin on an mbarrier phase (no watchdog: used where the wait sits in a hot unrolled loop)
 __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity) {

@@ -16,6 +16,10 @@
 // Per-angle constants live in __constant__ memory.
 #include "tmb_common.h"
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace tmb {
 
 // ------------------------------------------------------------------------------------------
@@ -26,25 +30,66 @@ namespace tmb {
 __constant__ float4 c_bp[MAX_ANGLES];
 __constant__ float4 c_fp[MAX_ANGLES];
 
-static uint64_t g_loaded_geom[64] = {0};  // per device: which table chunk sits in constant memory
+// One table per device, shared by every geometry, stream and host thread that uses the device.  Who may overwrite
+// it and when is tracked here: an upload waits -- on the device, through events, never on the host --
+// for every stream that launched kernels reading the current table, and a stream that finds "its" table already
+// resident waits for the upload if another stream issued it.
+struct TableState {
+  std::mutex mu;
+  uint64_t key = 0;                // geometry id * 4096 + chunk; 0 = nothing loaded
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t uploaded = nullptr;  // recorded after the two symbol copies
+  std::vector<std::pair<cudaStream_t, cudaEvent_t>> users;  // last kernel of each stream reading the table
+};
+static TableState g_table[64];
 
 int ensure_table(const tmb_geom *g, int a_begin, int a_count, cudaStream_t st) {
   // table chunk [a_begin, a_begin + a_count) of geometry g -> constant memory slots [0, a_count)
   static thread_local float4 hbp[MAX_ANGLES], hfp[MAX_ANGLES];
   int dev = 0;
   TMB_CUDA_CHECK(cudaGetDevice(&dev));
-  uint64_t key = g->id * 4096u + (uint64_t)(a_begin / MAX_ANGLES);
-  if (g_loaded_geom[dev & 63] == key) return TMB_OK;
-  // the previous upload's staging buffer may still be in flight on another geometry: the
-  // copies below are synchronous w.r.t. the host for pageable memory, so reuse is safe.
+  TableState &t = g_table[dev & 63];
+  std::lock_guard<std::mutex> lock(t.mu);
+  const uint64_t key = g->id * 4096u + (uint64_t)(a_begin / MAX_ANGLES);
+  if (t.key == key) {
+    if (st != t.upload_stream && t.uploaded) TMB_CUDA_CHECK(cudaStreamWaitEvent(st, t.uploaded, 0));
+    return TMB_OK;
+  }
+  // kernels of other streams may still read the table that is about to be replaced
+  for (auto &u : t.users)
+    if (u.first != st) TMB_CUDA_CHECK(cudaStreamWaitEvent(st, u.second, 0));
+  // (the copies below are synchronous w.r.t. the host for pageable memory, so the staging arrays can be reused)
   for (int i = 0; i < a_count; ++i) {
-    const float *t = g->table + (size_t)(a_begin + i) * 8;
-    hbp[i] = make_float4(t[0], t[1], t[2], 0.f);
-    hfp[i] = make_float4(t[3], t[4], t[5], t[7] == 0.f ? -t[6] : t[6]);
+    const float *tb = g->table + (size_t)(a_begin + i) * 8;
+    hbp[i] = make_float4(tb[0], tb[1], tb[2], 0.f);
+    hfp[i] = make_float4(tb[3], tb[4], tb[5], tb[7] == 0.f ? -tb[6] : tb[6]);
   }
   TMB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_bp, hbp, sizeof(float4) * a_count, 0, cudaMemcpyHostToDevice, st));
   TMB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_fp, hfp, sizeof(float4) * a_count, 0, cudaMemcpyHostToDevice, st));
-  g_loaded_geom[dev & 63] = key;
+  if (!t.uploaded) TMB_CUDA_CHECK(cudaEventCreateWithFlags(&t.uploaded, cudaEventDisableTiming));
+  TMB_CUDA_CHECK(cudaEventRecord(t.uploaded, st));
+  t.key = key;
+  t.upload_stream = st;
+  return TMB_OK;
+}
+
+// the kernels launched on `st` so far read the resident table: remember it for the next upload
+int table_used(cudaStream_t st) {
+  int dev = 0;
+  TMB_CUDA_CHECK(cudaGetDevice(&dev));
+  TableState &t = g_table[dev & 63];
+  std::lock_guard<std::mutex> lock(t.mu);
+  for (auto &u : t.users)
+    if (u.first == st) return cudaEventRecord(u.second, st) == cudaSuccess ? TMB_OK : TMB_ERR_CUDA;
+  if (t.users.size() >= 16) {  // more streams than anybody uses: fold the oldest into a device-wide wait
+    TMB_CUDA_CHECK(cudaEventSynchronize(t.users.front().second));
+    cudaEventDestroy(t.users.front().second);
+    t.users.erase(t.users.begin());
+  }
+  cudaEvent_t ev;
+  TMB_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  TMB_CUDA_CHECK(cudaEventRecord(ev, st));
+  t.users.emplace_back(st, ev);
   return TMB_OK;
 }
 
@@ -750,6 +795,8 @@ static int launch_bp(const tmb_geom *g, int subset, const float4 *sint, float *v
     k_bp<<<grid, BP_CONSUMERS + 32, 0, st>>>(a);
     rc = check_launch("k_bp");
     if (rc) return rc;
+    rc = table_used(st);
+    if (rc) return rc;
     j += cnt;
   }
   return TMB_OK;
@@ -824,6 +871,8 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
       k_fp<<<grid, FP_K + 32, smem, st>>>(a);
     }
     rc = check_launch("k_fp");
+    if (rc) return rc;
+    rc = table_used(st);
     if (rc) return rc;
     j += cnt;
   }

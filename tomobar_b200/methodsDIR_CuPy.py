@@ -254,9 +254,10 @@ class RecToolsDIRCuPy:
     def _fourier_inv_estimator(self, shape, **kwargs):
         """FOURIER_INV called with a shape tuple (after any axis swap: [detY, angles, detX]): replays the
         allocation sequence of the method above on the active ``DeviceMemStack`` and returns the shape of
-        the reconstruction.  cuFFT work areas are counted as one copy of the transform's output (an upper
-        bound for the power-of-two sizes used here); the caller's input array is counted like the
-        reference counts it (``data_dtype`` keyword, default float32)."""
+        the reconstruction.  The stages are the reference's ``*_estimator`` twins (methodsDIR_CuPy.py:547, 685,
+        837, 898, 968), each replaying THIS implementation's allocations of that stage.  cuFFT work areas are
+        counted as one copy of the transform's output (an upper bound for the power-of-two sizes used here); the
+        caller's input array is counted like the reference counts it (``data_dtype`` keyword, default float32)."""
         from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
 
         stack = DeviceMemStack.instance()
@@ -300,43 +301,83 @@ class RecToolsDIRCuPy:
         for b in (nproj * 4, nproj * 4, nproj * 8, nproj * 4):  # theta, sorted theta, int64 / int32 indices
             stack.malloc(b)
         stack.free(nproj * 8)
-        # STEP 0: filter (see _fourier_filter): `out`, then per slice chunk the padded rows, their rfft, the
-        # filtered spectrum and the irfft output, plus one work area per transform
+        tmp_p = self._fbp_filtering_estimator(data_n, n, nproj, nz, power_of_2_oversampling, oversampling_level)
+        if padded:
+            stack.free(padded)                        # `del data`: only our padded copy goes away
+        datac, fde = self._setup_backprojection_input_estimator(n, nproj, nz2, tmp_p)
+        self._fft_and_interpolation_estimator(datac, fde)
+        self.ifft_gathered_projections_estimator(n, nz2)
+        recon_shape = self.unpad_reconstructed_data_estimator(fde, n, raw_nz, odd_horiz, recon_size)
+        for b in (nproj * 4, nproj * 4, nproj * 4):
+            stack.free(b)
+        return recon_shape
+
+    # ---- the stage estimators (same names as the reference's; each returns the sizes the next stage needs) ----
+    def _fbp_filtering_estimator(self, raw_width, width, nproj, nz, power_of_2_oversampling=True, oversampling_level=4):
+        """STEP 0 (_fourier_filter; reference twin methodsDIR_CuPy.py:547-643): `out`, then per slice chunk the
+        edge-padded rows, their rfft, the filtered spectrum and the irfft output plus one work area per transform.
+        Returns the bytes of the filtered projections, which stay allocated."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
         if power_of_2_oversampling:
-            over = 2 ** math.ceil(math.log2(data_n * 3))
-            if n > over:
-                over = 2 ** math.ceil(math.log2(n))
+            over = 2 ** math.ceil(math.log2(raw_width * 3))
+            if width > over:
+                over = 2 ** math.ceil(math.log2(width))
         else:
-            over = max(int(oversampling_level * data_n), n)
-        tmp_p = nz * nproj * n * 4
+            over = max(int(oversampling_level * raw_width), width)
+        tmp_p = nz * nproj * width * 4
         stack.malloc(tmp_p)
         per = min(nz, max(1, (1 << 27) // (nproj * over)))
         rows_real, rows_cplx = per * nproj * over * 4, per * nproj * (over // 2 + 1) * 8
-        stack.malloc(rows_real)                       # edge-padded rows
+        stack.malloc(rows_real)                            # edge-padded rows
         stack.malloc(rows_cplx), stack.malloc(rows_cplx)   # rfft output + its work area
         stack.free(rows_cplx)
-        stack.malloc(rows_cplx)                       # filtered spectrum
-        stack.free(rows_cplx)                         # (the rfft output is released after the product)
+        stack.malloc(rows_cplx)                            # filtered spectrum
+        stack.free(rows_cplx)                              # (the rfft output is released after the product)
         stack.malloc(rows_real), stack.malloc(rows_real)   # irfft output + its work area
         stack.free(rows_real), stack.free(rows_cplx), stack.free(rows_real), stack.free(rows_real)
-        if padded:
-            stack.free(padded)                        # `del data`: only our padded copy goes away
-        # STEP 1: complex slice pairs and their 1-D FFT (out of place)
+        return tmp_p
+
+    def _setup_backprojection_input_estimator(self, n, nproj, nz2, tmp_p):
+        """STEP 1 (reference twin :685-699): the complex slice pairs replace the filtered projections; their 1-D
+        FFT runs out of place (output + work area).  Returns the bytes of (datac, fde)."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
         datac = nz2 * nproj * n * 8
         stack.malloc(datac)
         stack.free(tmp_p)
         stack.malloc(datac), stack.malloc(datac)      # FFT output + work area
         stack.free(datac), stack.free(datac)
-        # STEP 2: the oversampled Cartesian grid
-        fde = nz2 * (2 * n) * (2 * n) * 8
+        return datac, nz2 * (2 * n) * (2 * n) * 8
+
+    def _fft_and_interpolation_estimator(self, datac, fde):
+        """STEP 2 (reference twin :837-849): the oversampled Cartesian grid is allocated, gathered / scattered into,
+        and the polar samples are released.  No angle-range table here, whatever the centre size: the gather finds
+        its ranges on the fly."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
         stack.malloc(fde)
         stack.free(datac)
-        # STEP 3: inverse 2-D FFT in slice chunks (output chunk + work area)
+
+    def ifft_gathered_projections_estimator(self, n, nz2):
+        """STEP 3 (reference twin :898-918): the inverse 2-D FFT runs in slice chunks (output chunk + work area)."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
         chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))
         piece = chunk * (2 * n) * (2 * n) * 8
         stack.malloc(piece), stack.malloc(piece)
         stack.free(piece), stack.free(piece)
-        # STEP 4: the reconstruction
+
+    def unpad_reconstructed_data_estimator(self, fde, n, raw_nz, odd_horiz, recon_size):
+        """STEP 4 (reference twin :968-989): the reconstruction is allocated, the grid released; like the reference,
+        the result itself is not kept on the stack."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
         odd_recon = bool(recon_size % 2)
         um = (n - odd_horiz) // 2 - recon_size // 2
         up = (n - odd_horiz) // 2 + (recon_size + odd_recon) // 2
@@ -344,8 +385,7 @@ class RecToolsDIRCuPy:
         recon = int(np.prod(recon_shape)) * 4
         stack.malloc(recon)
         stack.free(fde)
-        for b in (nproj * 4, nproj * 4, nproj * 4, recon):  # like the reference, the result is not kept on the stack
-            stack.free(b)
+        stack.free(recon)
         return recon_shape
 
     def _fourier_filter(self, data, raw_width, width, power_of_2_oversampling, oversampling_level, filter_type,

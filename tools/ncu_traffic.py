@@ -1,5 +1,5 @@
-"""Turns an ncu report of the TV kernels into profiles/ncu_traffic_r01.json (DRAM bytes per launch):
-   python tools/ncu_traffic.py gpurun_out/prof_traffic.ncu-rep nz n"""
+"""Turns an ncu report of the TV / gather kernels into profiles/ncu_traffic_r02.json (DRAM bytes per launch):
+   python tools/ncu_traffic.py gpurun_out/prof_traffic.ncu-rep nz n      (k_fi_gather: nz = complex slices, n = 2 * width)"""
 import csv
 import io
 import json
@@ -16,7 +16,7 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 out = []
 for r in rows[2:]:
     name = r[idx["Kernel Name"]]
-    kern = next((k for k in ("k_pd_tv3d_f2s", "k_pd_tv3d_f2", "k_pd_tv3d_w", "k_rof_tv3d_w") if k in name), None)
+    kern = next((k for k in ("k_pd_tv3d_f2s", "k_pd_tv3d_f2", "k_pd_tv3d_w", "k_rof_tv3d_w", "k_fi_gather") if k in name), None)
     if kern is None:
         continue
     tot = 0.0
@@ -25,8 +25,11 @@ for r in rows[2:]:
     out.append({"kernel": kern, "half": "__half" in name, "voxels": nz * n * n, "dram_bytes_per_launch": tot,
                 "duration_ms_under_ncu": float(r[idx["gpu__time_duration.sum"]]) *
                 {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[idx["gpu__time_duration.sum"]]],
-                "source": os.path.basename(rep)})
-path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic_r01.json")
+                "source": os.path.basename(rep),
+                **{m: float(r[idx[m]]) for m in ("smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                                 "sm__warps_active.avg.pct_of_peak_sustained_active",
+                                                 "lts__t_sector_hit_rate.pct") if m in idx}})
+path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic_r02.json")
 old = []
 if os.path.exists(path):
     old = [o for o in json.load(open(path)) if (o["kernel"], o["half"], o["voxels"]) not in
