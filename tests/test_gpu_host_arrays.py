@@ -152,3 +152,32 @@ def test_fbp2d_mask_and_agreement_with_the_sinc_fbp(scan):  # :144-169
     sinc = _rec(data, angles).FBP(data, data_axes_labels_order=LABELS)[60][::-1]
     assert np.corrcoef(full.ravel(), sinc.ravel())[0, 1] > 0.97
     assert 0.7 < np.abs(full).sum() / np.abs(sinc).sum() < 1.4
+
+
+def test_fourier_inv_estimate_at_config4_within_5_percent():
+    """BASELINE.json config 4 (2048^2 x 128, 2000 angles): the dry-run estimate against torch's measured peak
+    (measured on B200: 14.982 GB both; tools/check_estimator.py)."""
+    import torch
+
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+    from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+    nz, nproj, n = 128, 2000, 2048
+    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+        pytest.skip("needs ~17 GB of device memory")
+    angles = np.linspace(0, np.pi, nproj, endpoint=False).astype(np.float32)
+    R = RecToolsDIRCuPy(n, 0, nz, 0.0, angles, n, device_projector=0)
+    with DeviceMemStack() as st:
+        assert R.FOURIER_INV((nz, nproj, n), data_dtype=np.float32) == (nz, n, n)
+    data = torch.rand((nz, nproj, n), device="cuda")
+    R.FOURIER_INV(data)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    before = torch.cuda.memory_allocated()
+    R.FOURIER_INV(data)
+    torch.cuda.synchronize()
+    measured = torch.cuda.max_memory_allocated() - before + data.numel() * 4
+    assert abs(measured / st.highwater - 1.0) < 0.05, (measured, st.highwater)
+    del data
+    torch.cuda.empty_cache()
