@@ -58,6 +58,9 @@ int tmb_geom_subset_row(const tmb_geom *g, int subset, int *out_bins /* [ceil(na
 int tmb_geom_table(const tmb_geom *g, float *out);
 /* number of kernels the forward projection of `subset` launches (launch accounting of benchmarks) */
 int tmb_geom_fp_launches(const tmb_geom *g, int subset);
+/* angles per CTA the forward projection of `subset` shares one staged window between (k_fpm); 0 = one angle per
+ * CTA (k_fp / k_fpq).  For tests and benchmarks: which kernel family a call runs. */
+int tmb_geom_fp_group(const tmb_geom *g, int subset);
 /* bytes of device scratch tmb_fp3d / tmb_bp3d / tmb_grad need.  The caller allocates it ONCE,
  * zero-fills it ONCE (the kernels keep the zero borders intact) and passes it to every call. */
 size_t tmb_geom_workspace_bytes(const tmb_geom *g);

@@ -81,17 +81,19 @@ def _close(a, b):
     assert np.max(np.abs(a - b)) <= 2e-6 * max(np.max(np.abs(b)), 1.0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6, 7, 10])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6, 7, 10, 12, 14])
 @pytest.mark.parametrize("shape,zrun,nonneg,aniso", [
     ((2, 3, 8), 2, False, False),
     ((5, 9, 124), 5, True, False),
     ((7, 18, 132), 3, False, False),
     ((6, 5, 244), 2, True, True),
     ((4, 5, 4), 1, False, False),
+    ((5, 45, 12), 2, True, False),   # several strips of 8 rows along y, the last one partial
 ])
 def test_whole_volume_kernels_on_the_cpu(shim, plain, variant, shape, zrun, nonneg, aniso):
     """0: k_pd_tv3d_f2 (the default, validated on the B200), 1: k_pd_tv3d_f2s (run on the B200 on five
     shapes), 2: k_pd_tv3d_f2s at four CTAs per SM, 4: with packets two rows ahead, 6: with L2 prefetches,
+    12 / 14: strips of 8 rows (14: packets two rows ahead),
     7 / 10: k_pd_tv3d_f2t, the TMA-fed variant with a ring of 4 / 8 stages (bulk copies as memcpy, mbarrier waits as
     warp barriers; lanes outside the volume read NaN-poisoned stage memory and must not reach a stored lane)."""
     inp, U, P = _case(shape, sum(shape))
@@ -154,8 +156,8 @@ def test_z_shard_kernel_with_peer_pointers_on_the_cpu(shim, plain, variant, shap
 
 
 @pytest.mark.parametrize("shape,zrun,nonneg,aniso", [((5, 9, 124), 5, True, False), ((7, 18, 132), 3, False, True),
-                                                     ((4, 5, 4), 1, False, False)])
-@pytest.mark.parametrize("variant", [5, 9])
+                                                     ((4, 5, 4), 1, False, False), ((3, 40, 8), 3, True, False)])
+@pytest.mark.parametrize("variant", [5, 9, 13])
 def test_first_pass_variant_on_the_cpu(shim, plain, variant, shape, zrun, nonneg, aniso):
     """k_pd_tv3d_f2s<PZERO> (hook 6's first pass of a prox call): the dual arrays are NOT read -- they hold
     NaN here -- and the input doubles as the primal variable; result == two plain iterations from P = 0."""

@@ -75,6 +75,21 @@ template <bool NN, bool AN> void lane_entry(int variant, const Args &a) {
       k_pd_tv3d_f2s<NN, AN, true, 3, 1, true>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt,
                                               a.theta, a.dx, a.dy, a.dz, a.zrun, a.gh);
       break;
+    case 12:  // strips of 8 rows, two CTAs of four warps per SM
+      k_pd_tv3d_f2s<NN, AN, false, 2, 1, false, false, 0, 0, 8, 4>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3,
+                                                                  a.sigma, a.tau, a.lt, a.theta, a.dx, a.dy, a.dz,
+                                                                  a.zrun, F2Ghost<false>{});
+      break;
+    case 13:  // strips of 6 rows, five warps per CTA, first pass of a prox call
+      k_pd_tv3d_f2s<NN, AN, false, 2, 1, true, false, 0, 0, 6, 5>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3,
+                                                                 a.sigma, a.tau, a.lt, a.theta, a.dx, a.dy, a.dz,
+                                                                 a.zrun, F2Ghost<false>{});
+      break;
+    case 14:  // strips of 8 rows, packets two rows ahead
+      k_pd_tv3d_f2s<NN, AN, false, 2, 2, false, false, 0, 0, 8, 4>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3,
+                                                                  a.sigma, a.tau, a.lt, a.theta, a.dx, a.dy, a.dz,
+                                                                  a.zrun, F2Ghost<false>{});
+      break;
     default:
       k_pd_tv3d_f2s<NN, AN, true, 3>(a.in, a.U, a.Uo, a.P1, a.P2, a.P3, a.Q1, a.Q2, a.Q3, a.sigma, a.tau, a.lt, a.theta,
                                      a.dx, a.dy, a.dz, a.zrun, a.gh);
@@ -87,7 +102,8 @@ template <bool NN, bool AN> void lane_entry(int variant, const Args &a) {
 // 6 k_pd_tv3d_f2s<L2PF> (prefetches are no-ops on the host: this checks their address arithmetic compiles and the
 //   rest of the kernel is untouched), 7 k_pd_tv3d_f2t (TMA-fed ring of 4 stages), 8 k_pd_tv3d_f2t<GHOST>,
 // 9 k_pd_tv3d_f2t<PZERO> with 2 stages, 10 k_pd_tv3d_f2t with a ring of 8 stages,
-// 11 k_pd_tv3d_f2s<GHOST, PZERO> (first pair of a sharded prox call: no dual variable read, here or in the ghosts)
+// 11 k_pd_tv3d_f2s<GHOST, PZERO> (first pair of a sharded prox call: no dual variable read, here or in the ghosts),
+// 12 / 14 k_pd_tv3d_f2s on strips of 8 rows (14: packets two rows ahead), 13 strips of 6 rows x 5 warps with PZERO
 extern "C" int shim_run_fused_tv(int variant, int nonneg, int aniso, const float *in, const float *U, float *Uo,
                                  const float *P1, const float *P2, const float *P3, float *Q1, float *Q2, float *Q3,
                                  float sigma, float tau, float lt, float theta, int dx, int dy, int dz, int zrun,
@@ -98,7 +114,10 @@ extern "C" int shim_run_fused_tv(int variant, int nonneg, int aniso, const float
   a.gh.lo = ghost_lo; a.gh.hi = ghost_hi;
   a.gh.U_lo = U_lo; a.gh.P1_lo = P1_lo; a.gh.P2_lo = P2_lo; a.gh.P3_lo = P3_lo; a.gh.in_lo = in_lo;
   a.gh.U_hi = U_hi; a.gh.P1_hi = P1_hi; a.gh.P2_hi = P2_hi; a.gh.P3_hi = P3_hi; a.gh.in_hi = in_hi;
-  const int gx = (dx + tmb::F2_OUT - 1) / tmb::F2_OUT, gy = (dy + tmb::F2_S * tmb::F2_WARPS - 1) / (tmb::F2_S * tmb::F2_WARPS);
+  // rows per strip and warps per CTA of the variant
+  const int vs = (variant == 12 || variant == 14) ? 8 : (variant == 13 ? 6 : tmb::F2_S);
+  const int vw = variant == 13 ? 5 : tmb::F2_WARPS;
+  const int gx = (dx + tmb::F2_OUT - 1) / tmb::F2_OUT, gy = (dy + vs * vw - 1) / (vs * vw);
   const int gz = (dz + zrun - 1) / zrun;
   auto lane_body = [&](int warp, int lane, int bx, int by, int bz, ShimWarp *w) {
     threadIdx = {unsigned(warp * 32 + lane), 0, 0};
@@ -125,7 +144,7 @@ extern "C" int shim_run_fused_tv(int variant, int nonneg, int aniso, const float
           for (auto &t : lanes) t.join();
           continue;
         }
-        for (int warp = 0; warp < tmb::F2_WARPS; ++warp) {
+        for (int warp = 0; warp < vw; ++warp) {
           std::memset(tmb::f2_smem, 0xff, sizeof(tmb::f2_smem));  // NaN-poison the slots
           ShimWarp w;
           std::vector<std::thread> lanes;

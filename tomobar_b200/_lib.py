@@ -31,6 +31,7 @@ SIGNATURES = {
     "tmb_geom_subset_row": (_i, [_vp, _i, _ip]),
     "tmb_geom_table": (_i, [_vp, C.POINTER(C.c_float)]),
     "tmb_geom_fp_launches": (_i, [_vp, _i]),
+    "tmb_geom_fp_group": (_i, [_vp, _i]),
     "tmb_geom_workspace_bytes": (_sz, [_vp]),
     "tmb_fp_set_kernel": (_i, [_i]),
     "tmb_fp_set_segment": (_i, [_i]),

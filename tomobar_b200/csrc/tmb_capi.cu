@@ -23,8 +23,8 @@ using namespace tmb;
 extern "C" int tmb_version(void) { return 100; }
 extern "C" int tmb_fp_set_kernel(int mode) {
   const int old = g_fp_kernel == 2 ? g_fpq_mode : g_fp_kernel;
-  g_fp_kernel = (mode == 1) ? 1 : ((mode >= 2 && mode <= 4) ? 2 : 0);
-  g_fpq_mode = (mode >= 2 && mode <= 4) ? mode : 0;
+  g_fp_kernel = (mode == 1) ? 1 : ((mode >= 2 && mode <= 7) ? 2 : 0);
+  g_fpq_mode = (mode >= 2 && mode <= 7) ? mode : 0;
   return old;
 }
 extern "C" const char *tmb_last_error(void) { return g_err.c_str(); }

@@ -16,6 +16,8 @@
 // Per-angle constants live in __constant__ memory.
 #include "tmb_common.h"
 
+#include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -655,6 +657,220 @@ __global__ void k_fp_finish(const FpArgs p, int nzc8) {
 }
 
 // ==========================================================================================
+// k_fpm: the Joseph march of k_fpq with NA neighbouring angles of the subset sharing ONE window.
+//
+// k_fpq is bound by the L2 -> shared-memory traffic (4.7 B per update: every volume sample a CTA stages
+// serves one angle and only the ~1 / |bstep| bins whose rays pass next to it).  Here a CTA stages one
+// (wider) window per volume line and marches up to NA angles through it, so a staged byte serves NA times
+// as many updates.  The angles of an ordered subset are degrees apart and their rays diverge along the
+// march, so the bins an angle contributes to a CTA are chosen PER ANGLE, such that all of them cross the
+// centre line of the CTA's line segment inside the same interval of D = (FQ_K - 0.5) * min |bstep|
+// positions ("tile" t of the group: r in [R0 + t D, R0 + (t + 1) D), r = position of a ray on the centre
+// line); away from the centre line the window grows by |m - mc| * (max alpha - min alpha), which the short
+// L2 segments keep small (host check: fpm_fits).  An angle's tiles partition its bins (same boundary
+// expression on both sides), each with at most FQ_K of them.  Angles of a group that march along the other
+// axis (the group straddles |sin| = |cos|) go through a second pass of the same CTA.
+// Arithmetic per (angle, bin, line) and the order of the line / segment sums are those of k_fpq:
+// the result is bit-identical (tests/test_gpu_projector.py).
+// ==========================================================================================
+constexpr int FM_W = 144;      // positions of a staged line (18 KB)
+constexpr int FM_G = 2;        // volume lines per pipeline stage
+constexpr int FM_STAGES = 3;
+constexpr size_t FM_SMEM = sizeof(float4) * FM_STAGES * FM_G * FM_W * FQ_CG;
+
+// what thread 0 works out per pass and every thread of the CTA then reads (keeps the consumers' registers
+// for the accumulators: 544 threads x 2 CTAs per SM leave 56 each)
+template <int NA> struct FmPass {
+  float alpha[NA], b0[NA], bstep[NA];
+  int k0[NA], cnt[NA];
+  unsigned act;   // angles of the pass
+  int total;      // bins of all angles in this tile (0: nothing to do)
+  int dir0;       // the pass marches along columns (V0)
+};
+
+template <int NA>
+__global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpm(const FpArgs p) {
+  extern __shared__ __align__(128) unsigned char fp_smem[];
+  // buf[stage][line][position][chunk]
+  float4(*buf)[FM_G][FM_W][FQ_CG] = reinterpret_cast<float4(*)[FM_G][FM_W][FQ_CG]>(fp_smem);
+  __shared__ int wst[FM_STAGES][FM_G], wln[FM_STAGES][FM_G];
+  __shared__ __align__(8) uint64_t full_bar[FM_STAGES], empty_bar[FM_STAGES];
+  __shared__ FmPass<NA> ps;
+
+  const int tid = threadIdx.x;
+  const int jg0 = (int)blockIdx.y * NA;      // first angle of the group, relative to j_begin
+  const int seg = (int)blockIdx.z % p.nseg;
+  const int zg = p.zg_first + (int)blockIdx.z / p.nseg;
+  const int m_lo = seg * p.seg_len, m_hi = min(p.n, m_lo + p.seg_len);  // this CTA's volume lines
+  const float half = 0.5f * (float)p.n;
+
+  if (tid == 0) {
+    for (int s = 0; s < FM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], FQ_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+
+  const int lane = tid & 31;
+  const int cc = tid & (FQ_CG - 1);  // z-chunk inside the group
+  const int kk = tid >> 3;           // bin of the tile (consumers)
+  const bool quant = p.quant != 0;
+  const int n_iter = (m_hi - m_lo + FM_G - 1) / FM_G;
+  int it_base = 0;  // pipeline iterations of the earlier pass (stages and phases carry on)
+
+  for (int pass = 0; pass < 2; ++pass) {
+    if (tid == 0) {
+      const int nag = min(NA, p.jc - jg0);  // angles of the group
+      const float xmc = (float)((m_lo + m_hi) >> 1) - half + 0.5f;  // centre line of the segment
+      float4 t[NA];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) t[a] = c_fp[p.a_first + (p.j_begin + jg0 + min(a, nag - 1)) * p.a_stride];
+      // angles of this pass: those marching along the same axis as the first (pass 0) / the others (pass 1)
+      unsigned act = 0;
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        if (a < nag && ((t[a].w < 0.f) == (t[0].w < 0.f)) == (pass == 0)) act |= 1u << a;
+      // tile of the pass: rays that cross the centre line at r in [lo, hi)
+      float R0 = 3.0e38f, bmin = 3.0e38f;
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        if (act & (1u << a)) {
+          const float c = fmaf(t[a].x, xmc, t[a].y);
+          R0 = fminf(R0, fminf(c, fmaf((float)(p.nu - 1), t[a].z, c)));
+          bmin = fminf(bmin, fabsf(t[a].z));
+        }
+      R0 -= 0.5f;  // no ray sits on the first boundary (the quotients below round)
+      const float D = ((float)FQ_K - 0.5f) * bmin;
+      const float lo = fmaf((float)blockIdx.x, D, R0), hi = fmaf((float)(blockIdx.x + 1), D, R0);
+      int total = 0;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        int k0 = 0, cnt = 0;
+        if (act & (1u << a)) {
+          const float c = fmaf(t[a].x, xmc, t[a].y), b = t[a].z;
+          float fa, fb;  // bins [fa, fb)
+          if (b > 0.f) { fa = ceilf((lo - c) / b); fb = ceilf((hi - c) / b); }
+          else { fa = floorf((c - hi) / -b) + 1.0f; fb = floorf((c - lo) / -b) + 1.0f; }
+          k0 = (int)fminf(fmaxf(fa, 0.f), (float)p.nu);
+          cnt = max((int)fminf(fmaxf(fb, 0.f), (float)p.nu) - k0, 0);
+        }
+        ps.alpha[a] = t[a].x; ps.b0[a] = t[a].y; ps.bstep[a] = t[a].z;
+        ps.k0[a] = k0; ps.cnt[a] = cnt;
+        if (cnt == 0) act &= ~(1u << a);
+        total += cnt;
+      }
+      ps.act = act; ps.total = total;
+      ps.dir0 = ((t[0].w < 0.f) == (pass == 0)) ? 1 : 0;
+    }
+    __syncthreads();  // (first pass: also publishes the mbarrier inits)
+    const unsigned act = ps.act;
+    if (ps.total > 0) {  // CTA-uniform
+      if (tid >= FQ_THREADS) {
+        if (tid == FQ_THREADS) {
+          const float4 *vsrc = ps.dir0 ? p.v0 : p.v1;
+          // per angle: beta of its first and last bin of the tile (the window of a line spans their positions)
+          float al[NA], ba[NA], bb[NA];
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            al[a] = ps.alpha[a];
+            ba[a] = fmaf((float)ps.k0[a], ps.bstep[a], ps.b0[a]);
+            bb[a] = fmaf((float)(ps.k0[a] + max(ps.cnt[a], 1) - 1), ps.bstep[a], ps.b0[a]);
+          }
+          for (int it = 0; it < n_iter; ++it) {
+            const int gi = it_base + it;
+            const int s = gi % FM_STAGES;
+            const uint32_t ph = (gi / FM_STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int m0 = m_lo + it * FM_G;
+            const int ng = min(FM_G, m_hi - m0);
+            uint32_t bytes = 0;
+            for (int gm = 0; gm < ng; ++gm) {
+              const float xm = (float)(m0 + gm) - half + 0.5f;
+              float wmin = 3.0e38f, wmax = -3.0e38f;
+#pragma unroll
+              for (int a = 0; a < NA; ++a)
+                if (act & (1u << a)) {
+                  const float ra = fmaf(al[a], xm, ba[a]), rb = fmaf(al[a], xm, bb[a]);
+                  wmin = fminf(wmin, fminf(ra, rb));
+                  wmax = fmaxf(wmax, fmaxf(ra, rb));
+                }
+              int ws = (int)floorf(fmaxf(wmin, -4.0e6f)) - 1;
+              ws = max(-QPAD, min(ws, p.n));
+              int wl = (int)floorf(fminf(wmax, 4.0e6f)) - ws + 2;
+              wl = max(2, min(wl, min(FM_W, p.n + QPAD - ws)));
+              wst[s][gm] = ws;
+              wln[s][gm] = wl;
+              bytes += (uint32_t)(wl * FQ_CG * sizeof(float4));
+            }
+            // the arrive releases the window starts to the consumers that acquire the completed phase
+            mbar_arrive_expect_tx(&full_bar[s], bytes);
+            for (int gm = 0; gm < ng; ++gm) {
+              const float4 *src = vsrc + (((size_t)zg * p.n + (m0 + gm)) * p.qp + (QPAD + wst[s][gm])) * FQ_CG;
+              bulk_g2s(&buf[s][gm][0][0], src, (uint32_t)(wln[s][gm] * FQ_CG * sizeof(float4)), &full_bar[s]);
+            }
+          }
+        }
+      } else {
+        float al[NA], beta[NA];
+        float4 acc[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          al[a] = ps.alpha[a];
+          beta[a] = fmaf((float)(ps.k0[a] + kk), ps.bstep[a], ps.b0[a]);
+          acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int it = 0; it < n_iter; ++it) {
+          const int gi = it_base + it;
+          const int s = gi % FM_STAGES;
+          const uint32_t ph = (gi / FM_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          const int m0 = m_lo + it * FM_G;
+          const int ng = min(FM_G, m_hi - m0);
+          // (float)(m0 + gm) - half + 0.5f: integers and halves below 2^24 are exact, so base + gm is identical
+          const float xbase = (float)m0 - half + 0.5f;
+          const float4 *sbuf = &buf[s][0][0][cc];
+#pragma unroll
+          for (int gm = 0; gm < FM_G; ++gm) {
+            if (gm < ng) {
+              const int wsl = wst[s][gm], wl2 = wln[s][gm] - 2;
+              const float x = xbase + (float)gm;
+#pragma unroll
+              for (int a = 0; a < NA; ++a) {
+                if (act & (1u << a)) {
+                  const float rho = fmaf(al[a], x, beta[a]);
+                  const int ifl = __float2int_rd(rho);
+                  float f = rho - (float)ifl;
+                  if (quant) f = ((f * 256.0f + 12582912.0f) - 12582912.0f) * (1.0f / 256.0f);
+                  const float g = 1.0f - f;
+                  const int i = max(0, min(ifl - wsl, wl2));
+                  const float4 *e = sbuf + (gm * FM_W + i) * FQ_CG;
+                  lerp_acc(acc[a], g, f, e[0], e[FQ_CG]);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        const int zc = zg * FQ_CG + cc;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          if ((act & (1u << a)) && kk < ps.cnt[a]) {
+            const int k = ps.k0[a] + kk, jl = jg0 + a;
+            // raw partial sum of this line segment (k_fpm always runs segmented; k_fp_finish has the epilogue)
+            const int nzc8 = (int)(gridDim.z / p.nseg) * FQ_CG + p.zg_first * FQ_CG;
+            p.part[(((size_t)seg * nzc8 + zc) * p.jc + jl) * p.nu_pad + k] = acc[a];
+          }
+        }
+      }
+      it_base += n_iter;
+    }
+    __syncthreads();  // everybody is done with `ps` before thread 0 rewrites it
+  }
+}
+
+// ==========================================================================================
 // residual post-pass for the robust / ring-artefact data terms (extension, see DESIGN.md: the
 // reference snapshot only keeps their call sites, Demos/methods_IR_legacy/DemoFISTA_artifacts2D.py:
 // 197,307-309).  Runs on the residual the forward projector's epilogue left in S_int, one thread
@@ -745,7 +961,9 @@ __global__ void k_resid_post(const PostArgs p) {
 // ==========================================================================================
 // test hook (tmb_fp_set_kernel): 0 / 2 = k_fpq<1> with line segments, 3 = k_fpq<2> (two z-groups per
 // CTA, no segments), 4 = k_fpq<1> without segments
+// 5 / 6 / 7 = k_fpm (groups of at most 2 / 3 / 4 angles sharing a window) where its windows fit
 int g_fpq_mode = 0;
+static int g_fpm_default = 0;  // group size of k_fpm when no hook is set (0: k_fpq)
 static int subset_first(const tmb_geom *g, int subset) { return subset < 0 ? 0 : subset; }
 static int subset_stride(const tmb_geom *g, int subset) { return subset < 0 ? 1 : g->os_number; }
 int subset_size(const tmb_geom *g, int subset) {
@@ -800,6 +1018,76 @@ static int launch_bp(const tmb_geom *g, int subset, const float4 *sint, float *v
     j += cnt;
   }
   return TMB_OK;
+}
+
+// k_fpm: does a group size of NA angles fit the staged window for local angles [jbeg, jbeg + jc) of the
+// subset, and how many tiles does the widest group need?  Mirrors the kernel's tile geometry in double
+// precision with a margin (a tile too many costs an empty CTA; a window too narrow would lose samples).
+static bool fpm_fits(const tmb_geom *g, int first, int stride, int jbeg, int jc, int NA, int seg_len, int nseg,
+                     int *tiles_out) {
+  const int n = g->d.n, nu = g->d.nu;
+  const double half = 0.5 * n;
+  int tiles = 1;
+  for (int g0 = 0; g0 < jc; g0 += NA) {
+    const int nag = std::min(NA, jc - g0);
+    const float *t0 = g->table + (size_t)(first + (jbeg + g0) * stride) * 8;
+    for (int pass = 0; pass < 2; ++pass) {
+      double amin = 1e30, amax = -1e30, bmin = 1e30;
+      int nact = 0;
+      for (int a = 0; a < nag; ++a) {
+        const float *t = g->table + (size_t)(first + (jbeg + g0 + a) * stride) * 8;
+        if (((t[7] == t0[7]) ? 0 : 1) != pass) continue;
+        ++nact;
+        amin = std::min(amin, (double)t[3]); amax = std::max(amax, (double)t[3]);
+        bmin = std::min(bmin, std::fabs((double)t[5]));
+      }
+      if (!nact) continue;
+      const double D = (FQ_K - 0.5) * bmin;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int m_lo = sg * seg_len, m_hi = std::min(n, m_lo + seg_len);
+        const double xmc = (double)((m_lo + m_hi) >> 1) - half + 0.5;
+        double rmin = 1e30, rmax = -1e30;
+        for (int a = 0; a < nag; ++a) {
+          const float *t = g->table + (size_t)(first + (jbeg + g0 + a) * stride) * 8;
+          if (((t[7] == t0[7]) ? 0 : 1) != pass) continue;
+          const double c = t[3] * xmc + t[4], e = c + (nu - 1) * (double)t[5];
+          rmin = std::min(rmin, std::min(c, e)); rmax = std::max(rmax, std::max(c, e));
+        }
+        tiles = std::max(tiles, (int)std::floor((rmax - rmin + 0.5) / D) + 2);
+        const double reach = std::max(xmc - (m_lo - half + 0.5), (m_hi - 1 - half + 0.5) - xmc);
+        if (D + reach * (amax - amin) + 6.0 > FM_W) return false;
+      }
+    }
+  }
+  *tiles_out = tiles;
+  return true;
+}
+
+// group size of k_fpm for these angles: the largest allowed one whose windows fit (0: k_fpq)
+static int fpm_group(const tmb_geom *g, int first, int stride, int jbeg, int jc, int seg_len, int nseg, int *tiles) {
+  // test hook (tmb_fp_set_kernel): 5 / 6 / 7 = k_fpm with groups of at most 2 / 3 / 4 angles, 2 = k_fpq only
+  const int na_max = g_fpq_mode >= 5 ? g_fpq_mode - 3 : (g_fpq_mode == 0 ? g_fpm_default : 0);
+  for (int na = na_max; na >= 2; --na)
+    if (fpm_fits(g, first, stride, jbeg, jc, na, seg_len, nseg, tiles)) return na;
+  return 0;
+}
+
+template <int NA>
+static void launch_fpm(const FpArgs &a, int tiles, int jc, int gz, cudaStream_t st) {
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(k_fpm<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM);
+  k_fpm<NA><<<dim3(tiles, (jc + NA - 1) / NA, gz), FQ_THREADS + 32, FM_SMEM, st>>>(a);
+}
+
+// k_fpq<1> or, where its windows fit, the multi-angle k_fpm for local angles [a.j_begin, + jc)
+static void launch_fpq_or_fpm(const tmb_geom *g, FpArgs &a, int first, int stride, int jc, int gz, size_t smem_q1,
+                              cudaStream_t st) {
+  int tiles = 0;
+  const int na = fpm_group(g, first, stride, a.j_begin, jc, a.seg_len, a.nseg, &tiles);
+  if (na == 4) launch_fpm<4>(a, tiles, jc, gz, st);
+  else if (na == 3) launch_fpm<3>(a, tiles, jc, gz, st);
+  else if (na == 2) launch_fpm<2>(a, tiles, jc, gz, st);
+  else k_fpq<1><<<dim3((g->d.nu + FQ_K - 1) / FQ_K, jc, gz), FQ_THREADS + 32, smem_q1, st>>>(a);
 }
 
 static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const float4 *v1, float *sino, float4 *sint,
@@ -861,7 +1149,7 @@ static int launch_fp(const tmb_geom *g, int subset, const float4 *v0, const floa
         for (int c0 = 0; c0 < cnt; c0 += g->part_angles) {
           const int jc = min(g->part_angles, cnt - c0);
           a.j_begin = j + c0; a.jc = jc;
-          k_fpq<1><<<dim3(tiles, jc, g->d.nzg * g->nseg), FQ_THREADS + 32, smem_q1, st>>>(a);
+          launch_fpq_or_fpm(g, a, first, stride, jc, g->d.nzg * g->nseg, smem_q1, st);
           k_fp_finish<<<dim3((g->d.nu + 127) / 128, jc, nzc8), 128, 0, st>>>(a, nzc8);
         }
         a.j_begin = j;
@@ -955,6 +1243,18 @@ extern "C" int tmb_grad_ext(tmb_geom *g, int subset, const float *x, const float
   rc = check_launch("k_resid_post");
   if (rc) return rc;
   return launch_bp(g, subset, ws.s, grad, st);
+}
+
+extern "C" int tmb_geom_fp_group(const tmb_geom *g, int subset) {
+  if (!g || subset < -1 || subset >= g->os_number) return TMB_ERR_ARG;
+  if (!g->fp_q || g->nseg <= 1) return 0;
+  const int na_loc = subset_size(g, subset);
+  const int first = subset < 0 ? 0 : subset, stride = subset < 0 ? 1 : g->os_number;
+  int cnt = 0;  // first constant-table / partial-buffer chunk, as launch_fp cuts it
+  const int chunk_base = (first / MAX_ANGLES) * MAX_ANGLES;
+  while (cnt < na_loc && first + cnt * stride < chunk_base + MAX_ANGLES) ++cnt;
+  int tiles = 0;
+  return fpm_group(g, first, stride, 0, std::min(cnt, g->part_angles), g->seg_len, g->nseg, &tiles);
 }
 
 // Number of kernels the forward projection of `subset` launches (k_fp / k_fpq per constant-table and

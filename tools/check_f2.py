@@ -25,7 +25,7 @@ def main():
         v = torch.randn(*shape, device="cuda") * 0.05
         for its, nonneg, method in ((2, 1, 0), (7, 0, 0), (4, 1, 1)):
             b = run(3, v, its, None, nonneg, method)
-            for mode in (0, 5, 6, 7, 8, 9, 10, 13):
+            for mode in (0, 5, 6, 7, 8, 9, 10, 13, 22, 23, 24, 25, 26, 27, 28, 29):
                 a = run(mode, v, its, None, nonneg, method)
                 d = (a - b).abs().max().item() / b.abs().max().item()
                 print(f"mode {mode} shape={shape} its={its} nonneg={nonneg} methodTV={method}: rel max diff {d:.3e} "
@@ -37,7 +37,7 @@ def main():
         v = torch.randn(nz, n, n, device="cuda") * 0.02
         out = torch.empty_like(v)
         ref = None
-        for mode, name in ((3, "strip-reg"), (5, "fused-2"), (6, "fused-2s"), (7, "fused-2s/4"), (8, "fused-2s/pf2"), (9, "fused-2s/p0"), (10, "fused-2s/l2pf"), (13, "fused-2s/p0+l2pf"), (0, "default"), (14, "DIAG mem-only"), (15, "DIAG L2-resident")):
+        for mode, name in ((3, "strip-reg"), (5, "fused-2"), (6, "fused-2s"), (7, "fused-2s/4"), (8, "fused-2s/pf2"), (9, "fused-2s/p0"), (10, "fused-2s/l2pf"), (13, "fused-2s/p0+l2pf"), (0, "default"), (22, "tall 8x4w"), (23, "tall 8x4w/pf2"), (24, "tall 6x5w"), (25, "tall 8x2w x4"), (26, "cta 2x2"), (27, "cta 4x1"), (28, "cta 3x1 x4"), (29, "cta 6x1 x2"), (14, "DIAG mem-only"), (15, "DIAG L2-resident")):
             run(mode, v, its, out)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
