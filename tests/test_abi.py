@@ -103,3 +103,28 @@ def test_pd_tv_launch_accounting_needs_no_gpu():
             assert lib.tmb_pd_tv_launches(16, 64, 64, 10, 0) == want, mode
     finally:
         lib.tmb_tv_set_simple_kernels(0)
+
+
+def test_forward_projector_group_size_host_logic():
+    """Which forward-projector family a geometry gets (host arithmetic of tmb_geom_fp_group, no GPU): the
+    multi-angle kernel k_fpm with groups of 4 at BASELINE.json's sizes, smaller groups / one angle per CTA
+    (0) where neighbouring subset angles diverge by more than its staged window holds, and stacks of at
+    most 16 slices or volumes of a single line segment stay with k_fp / k_fpq."""
+    from tomobar_b200._lib import lib
+    from tomobar_b200.projector import ProjTools3D
+
+    def group(nz, n, na, os_n, sub=0):
+        angles = np.linspace(0, np.pi, na, endpoint=False).astype(np.float32)
+        P = ProjTools3D(n, 0, nz, angles, 0.0, n, "gpu", 0, os_n)
+        return lib.tmb_geom_fp_group(P._g, sub)
+
+    assert group(512, 2048, 1800, 24) == 4      # headline
+    assert group(64, 2048, 1800, 24, 23) == 4   # a z-shard of it
+    assert group(256, 1024, 900, 6) == 4        # config 2
+    assert group(384, 1536, 1500, 6) == 4       # config 5
+    assert group(8, 2048, 1800, 24) == 0        # <= 16 slices: k_fp
+    assert group(64, 256, 180, 1) == 0          # one line segment: k_fpq writes the sinogram itself
+    coarse = group(64, 2048, 96, 8)             # subset angles 15 degrees apart: windows too wide for any group
+    assert coarse == 0
+    mid = group(64, 2048, 300, 12)              # 7.2 degrees apart: smaller groups
+    assert 2 <= mid < 4

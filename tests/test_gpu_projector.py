@@ -164,8 +164,9 @@ def test_linearity_and_zero_at_scale():
                                              (64, 40, 64, 12, None)])
 def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
     """k_fp (8 slices per thread) and k_fpq (bank-conflict-free 32-slice blocks): one block per CTA
-    (mode 4), two (mode 3) are bit-identical to k_fp; the line-segmented default (mode 2, segments
-    forced short here) adds its partial sums in a different order and agrees to fp32 rounding."""
+    (mode 4), two (mode 3) are bit-identical to k_fp; the line-segmented k_fpq (mode 2, segments
+    forced short here) adds its partial sums in a different order and agrees to fp32 rounding; the
+    multi-angle k_fpm (modes 5-7, the default where its windows fit) is bit-identical to mode 2."""
     from tomobar_b200._lib import lib
     from tomobar_b200.projector import ProjTools3D
 
@@ -174,9 +175,9 @@ def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
     b = torch.randn((nz, na, nu), device="cuda", generator=g)
     w = torch.rand((nz, na, nu), device="cuda", generator=g)
     res = {}
-    for mode in (1, 2, 3, 4):
+    for mode in (1, 2, 3, 4, 5, 6, 7):
         lib.tmb_fp_set_kernel(mode)
-        lib.tmb_fp_set_segment(24 if mode == 2 else 0)
+        lib.tmb_fp_set_segment(24 if mode in (2, 5, 6, 7) else 0)
         try:
             P = ProjTools3D(nu, 0, nz, _angles(na), 0.5, n, "gpu", 0, os_n)
             sub = None if os_n is None else os_n - 1
@@ -190,3 +191,8 @@ def test_forward_projector_kernels_agree(nz, n, nu, na, os_n):
             assert torch.equal(a, c)
     for a, c in zip(res[1][:2], res[2][:2]):
         assert rel_max(c.cpu().numpy(), a.cpu().numpy()) < 2e-6
+    # k_fpm (2 / 3 / 4 angles of the subset per CTA sharing one window): same arithmetic and summation order as
+    # the segmented k_fpq
+    for mode in (5, 6, 7):
+        for a, c in zip(res[2], res[mode]):
+            assert torch.equal(a, c)

@@ -688,12 +688,29 @@ template <int NA> struct FmPass {
   int dir0;       // the pass marches along columns (V0)
 };
 
-template <int NA>
+// one (line, angle) update of a consumer thread: index and weight exactly as k_fpq computes them (QUANT: ASTRA's
+// 8-bit texture weights, rounded with the 1.5 * 2^23 trick instead of a conversion-pipe instruction).
+// (Taking both from one conversion, q = rint(256 rho), saves two instructions but is not the same number for
+// rho in (-1, 0), the one interval where rho - floor(rho) rounds -- measured: one bin off by 1/256 of a sample.)
+template <bool QUANT>
+__device__ __forceinline__ void fm_update(float4 &acc, float al, float be, float x, int wsl, int wl2,
+                                          const float4 *line) {
+  const float rho = fmaf(al, x, be);
+  const int ifl = __float2int_rd(rho);
+  float f = rho - (float)ifl;
+  if constexpr (QUANT) f = ((f * 256.0f + 12582912.0f) - 12582912.0f) * (1.0f / 256.0f);
+  const float g = 1.0f - f;
+  const int i = max(0, min(ifl - wsl, wl2));
+  const float4 *e = line + i * FQ_CG;
+  lerp_acc(acc, g, f, e[0], e[FQ_CG]);
+}
+
+template <int NA, bool QUANT>
 __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpm(const FpArgs p) {
   extern __shared__ __align__(128) unsigned char fp_smem[];
   // buf[stage][line][position][chunk]
   float4(*buf)[FM_G][FM_W][FQ_CG] = reinterpret_cast<float4(*)[FM_G][FM_W][FQ_CG]>(fp_smem);
-  __shared__ int wst[FM_STAGES][FM_G], wln[FM_STAGES][FM_G];
+  __shared__ int2 wsl_s[FM_STAGES][FM_G];  // per staged line: first position, positions - 2
   __shared__ __align__(8) uint64_t full_bar[FM_STAGES], empty_bar[FM_STAGES];
   __shared__ FmPass<NA> ps;
 
@@ -715,7 +732,6 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpm(const FpArgs p) {
   const int lane = tid & 31;
   const int cc = tid & (FQ_CG - 1);  // z-chunk inside the group
   const int kk = tid >> 3;           // bin of the tile (consumers)
-  const bool quant = p.quant != 0;
   const int n_iter = (m_hi - m_lo + FM_G - 1) / FM_G;
   int it_base = 0;  // pipeline iterations of the earlier pass (stages and phases carry on)
 
@@ -797,17 +813,17 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpm(const FpArgs p) {
                 }
               int ws = (int)floorf(fmaxf(wmin, -4.0e6f)) - 1;
               ws = max(-QPAD, min(ws, p.n));
-              int wl = (int)floorf(fminf(wmax, 4.0e6f)) - ws + 2;
+              int wl = (int)floorf(fminf(wmax, 4.0e6f)) - ws + 2;  // floor(wmax) + 1 is the last sample read
               wl = max(2, min(wl, min(FM_W, p.n + QPAD - ws)));
-              wst[s][gm] = ws;
-              wln[s][gm] = wl;
+              wsl_s[s][gm] = make_int2(ws, wl - 2);
               bytes += (uint32_t)(wl * FQ_CG * sizeof(float4));
             }
             // the arrive releases the window starts to the consumers that acquire the completed phase
             mbar_arrive_expect_tx(&full_bar[s], bytes);
             for (int gm = 0; gm < ng; ++gm) {
-              const float4 *src = vsrc + (((size_t)zg * p.n + (m0 + gm)) * p.qp + (QPAD + wst[s][gm])) * FQ_CG;
-              bulk_g2s(&buf[s][gm][0][0], src, (uint32_t)(wln[s][gm] * FQ_CG * sizeof(float4)), &full_bar[s]);
+              const int2 w = wsl_s[s][gm];
+              const float4 *src = vsrc + (((size_t)zg * p.n + (m0 + gm)) * p.qp + (QPAD + w.x)) * FQ_CG;
+              bulk_g2s(&buf[s][gm][0][0], src, (uint32_t)((w.y + 2) * FQ_CG * sizeof(float4)), &full_bar[s]);
             }
           }
         }
@@ -820,33 +836,34 @@ __global__ void __launch_bounds__(FQ_THREADS + 32, 2) k_fpm(const FpArgs p) {
           beta[a] = fmaf((float)(ps.k0[a] + kk), ps.bstep[a], ps.b0[a]);
           acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        const bool full = act == (1u << NA) - 1u;
         for (int it = 0; it < n_iter; ++it) {
           const int gi = it_base + it;
           const int s = gi % FM_STAGES;
           const uint32_t ph = (gi / FM_STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (!mbar_try_wait(&full_bar[s], ph)) mbar_wait(&full_bar[s], ph);
           const int m0 = m_lo + it * FM_G;
           const int ng = min(FM_G, m_hi - m0);
           // (float)(m0 + gm) - half + 0.5f: integers and halves below 2^24 are exact, so base + gm is identical
           const float xbase = (float)m0 - half + 0.5f;
           const float4 *sbuf = &buf[s][0][0][cc];
+          if (full && ng == FM_G) {  // the common case as one basic block: all angles of the group, all lines
 #pragma unroll
-          for (int gm = 0; gm < FM_G; ++gm) {
-            if (gm < ng) {
-              const int wsl = wst[s][gm], wl2 = wln[s][gm] - 2;
+            for (int gm = 0; gm < FM_G; ++gm) {
+              const int2 w = wsl_s[s][gm];
               const float x = xbase + (float)gm;
 #pragma unroll
-              for (int a = 0; a < NA; ++a) {
-                if (act & (1u << a)) {
-                  const float rho = fmaf(al[a], x, beta[a]);
-                  const int ifl = __float2int_rd(rho);
-                  float f = rho - (float)ifl;
-                  if (quant) f = ((f * 256.0f + 12582912.0f) - 12582912.0f) * (1.0f / 256.0f);
-                  const float g = 1.0f - f;
-                  const int i = max(0, min(ifl - wsl, wl2));
-                  const float4 *e = sbuf + (gm * FM_W + i) * FQ_CG;
-                  lerp_acc(acc[a], g, f, e[0], e[FQ_CG]);
-                }
+              for (int a = 0; a < NA; ++a) fm_update<QUANT>(acc[a], al[a], beta[a], x, w.x, w.y, sbuf + gm * FM_W * FQ_CG);
+            }
+          } else {
+#pragma unroll
+            for (int gm = 0; gm < FM_G; ++gm) {
+              if (gm < ng) {
+                const int2 w = wsl_s[s][gm];
+                const float x = xbase + (float)gm;
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+                  if (act & (1u << a)) fm_update<QUANT>(acc[a], al[a], beta[a], x, w.x, w.y, sbuf + gm * FM_W * FQ_CG);
               }
             }
           }
@@ -963,7 +980,7 @@ __global__ void k_resid_post(const PostArgs p) {
 // CTA, no segments), 4 = k_fpq<1> without segments
 // 5 / 6 / 7 = k_fpm (groups of at most 2 / 3 / 4 angles sharing a window) where its windows fit
 int g_fpq_mode = 0;
-static int g_fpm_default = 0;  // group size of k_fpm when no hook is set (0: k_fpq)
+static int g_fpm_default = 4;  // largest group of k_fpm when no hook is set (measured: profiles/fp_multi_angle_r02.txt)
 static int subset_first(const tmb_geom *g, int subset) { return subset < 0 ? 0 : subset; }
 static int subset_stride(const tmb_geom *g, int subset) { return subset < 0 ? 1 : g->os_number; }
 int subset_size(const tmb_geom *g, int subset) {
@@ -1075,8 +1092,13 @@ static int fpm_group(const tmb_geom *g, int first, int stride, int jbeg, int jc,
 template <int NA>
 static void launch_fpm(const FpArgs &a, int tiles, int jc, int gz, cudaStream_t st) {
   static PerDeviceOnce attr;
-  if (attr.first()) cudaFuncSetAttribute(k_fpm<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM);
-  k_fpm<NA><<<dim3(tiles, (jc + NA - 1) / NA, gz), FQ_THREADS + 32, FM_SMEM, st>>>(a);
+  if (attr.first()) {
+    cudaFuncSetAttribute(k_fpm<NA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM);
+    cudaFuncSetAttribute(k_fpm<NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM);
+  }
+  const dim3 grid(tiles, (jc + NA - 1) / NA, gz);
+  if (a.quant) k_fpm<NA, true><<<grid, FQ_THREADS + 32, FM_SMEM, st>>>(a);
+  else k_fpm<NA, false><<<grid, FQ_THREADS + 32, FM_SMEM, st>>>(a);
 }
 
 // k_fpq<1> or, where its windows fit, the multi-angle k_fpm for local angles [a.j_begin, + jc)

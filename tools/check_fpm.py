@@ -12,11 +12,11 @@ from tomobar_b200._lib import lib  # noqa: E402
 from tomobar_b200.projector import ProjTools3D  # noqa: E402
 
 
-def fp(mode, seg, nz, n, nu, angles, cor, os_n, sub, vol):
+def fp(mode, seg, nz, n, nu, angles, cor, os_n, sub, vol, quant=True):
     lib.tmb_fp_set_kernel(mode)
     lib.tmb_fp_set_segment(seg)
     try:
-        P = ProjTools3D(nu, 0, nz, angles, cor, n, "gpu", 0, os_n)
+        P = ProjTools3D(nu, 0, nz, angles, cor, n, "gpu", 0, os_n, quantise_weights=quant)
         grp = lib.tmb_geom_fp_group(P._g, -1 if os_n is None else sub)
         out = P._forwprojCuPy(vol) if os_n is None else P._forwprojOSCuPy(vol, sub)
         return out, grp
@@ -39,14 +39,15 @@ def main():
     for nz, n, nu, na, span, cor, os_n, sub, seg in cases:
         angles = np.linspace(0, span, na, endpoint=False).astype(np.float32)
         vol = torch.randn((nz, n, n), device="cuda")
-        ref, _ = fp(2, seg, nz, n, nu, angles, cor, os_n, sub, vol)
-        for mode in (5, 6, 7):
-            out, grp = fp(mode, seg, nz, n, nu, angles, cor, os_n, sub, vol)
-            eq = torch.equal(out, ref)
-            d = (out - ref).abs().max().item() / ref.abs().max().item()
-            bad += (not eq)
-            print(f"mode {mode} group={grp} nz={nz} n={n} nu={nu} na={na} os={os_n} seg={seg}: bit-equal={eq} rel {d:.2e}",
-                  flush=True)
+        for quant in (True, False):
+            ref, _ = fp(2, seg, nz, n, nu, angles, cor, os_n, sub, vol, quant)
+            for mode in (5, 6, 7):
+                out, grp = fp(mode, seg, nz, n, nu, angles, cor, os_n, sub, vol, quant)
+                eq = torch.equal(out, ref)
+                d = (out - ref).abs().max().item() / ref.abs().max().item()
+                bad += (not eq)
+                print(f"mode {mode} group={grp} quant={quant} nz={nz} n={n} nu={nu} na={na} os={os_n} seg={seg}: "
+                      f"bit-equal={eq} rel {d:.2e}", flush=True)
     print("MISMATCHES", bad, flush=True)
     if len(sys.argv) > 1:
         for nz, n, na, os_n in ((512, 2048, 1800, 24), (256, 1024, 900, 6), (64, 2048, 1800, 24)):
