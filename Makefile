@@ -8,7 +8,7 @@ LIB := tomobar_b200/libtmb.so
 
 all: $(LIB)
 
-%.o: %.cu tomobar_b200/csrc/tmb_common.h tomobar_b200/csrc/tmb_tv_fused.cuh include/tmb.h
+%.o: %.cu tomobar_b200/csrc/tmb_common.h tomobar_b200/csrc/tmb_tv_fused.cuh tomobar_b200/csrc/tmb_tv_common.cuh include/tmb.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
