@@ -109,3 +109,40 @@ def test_fourier_inv_scatter_branches_vs_reference_kernels(scan, center_size):
     full = RecToolsDIRCuPy(detX, 0, nz, 0.0, angles, detX, device_projector=0).FOURIER_INV(d).cpu().numpy()
     # scatter and gather formulations are NOT numerically equal (3.7 % apart in rel-L2 there)
     assert rel_l2(got, full) < 0.1
+
+
+@pytest.mark.parametrize("n,na,nz,span,center", [(362, 241, 10, math.pi, None), (256, 180, 6, 2 * math.pi, None),
+                                                  (200, 97, 4, math.pi, 224)])
+def test_tile_staged_gather_is_bit_identical(n, na, nz, span, center):
+    """k_fi_gather_s (hook 2: the polar samples of a 16 x 8 tile of grid points staged in shared memory, the tile's
+    angle range walked in batches) visits every (point, line, sample) of k_fi_gather (hook 1) in the same order:
+    the grids are bit-identical, on the whole grid and on a centre square."""
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr
+
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    nz2 = nz // 2
+    theta = torch.as_tensor(-np.linspace(0, span, na, endpoint=False), dtype=torch.float32, device=dev)
+    sorted_theta, sorted_idx = torch.sort(theta)
+    sorted_idx = sorted_idx.to(torch.int32)
+    g = torch.Generator(device="cuda").manual_seed(n)
+    datac = torch.view_as_complex(torch.randn((nz2, na, n, 2), device=dev, generator=g))
+    mu = -np.log(1e-4) / (2 * n * n)
+    m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(1e-4) + (mu * n) * (mu * n) / 4)))
+    out = {}
+    for mode in (1, 2):
+        fde = torch.zeros((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+        old = lib.tmb_fi_set_gather(mode)
+        try:
+            if center is None:
+                check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
+                                        float(np.float32(mu)), n, na, nz2, st), "tmb_fi_gather")
+            else:
+                check(lib.tmb_fi_gather_center(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
+                                               float(np.float32(mu)), n, na, nz2, center, st), "tmb_fi_gather_center")
+        finally:
+            lib.tmb_fi_set_gather(old)
+        out[mode] = torch.view_as_real(fde)
+    assert torch.isfinite(out[2]).all() and out[1].abs().max() > 0
+    assert torch.equal(out[1], out[2])

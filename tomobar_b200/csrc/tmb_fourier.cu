@@ -187,6 +187,185 @@ __global__ void __launch_bounds__(128)
     if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = make_float2(acc[s].x * sg, acc[s].y * sg);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_fi_gather_s: the same gather with the polar samples of a TILE of grid points staged in shared memory.
+//
+// k_fi_gather is bound by the memory transactions of its loads, not by the weight arithmetic (profiles/
+// gather_z_interleaved_r02.txt): every polar sample is read by the ~40 grid points within the Gaussian's support,
+// each time as its own L1 / L2 access.  Here the 128 threads of a CTA (a 32 x 4 tile of grid points, FI_SC complex
+// slices) walk the angle range of the WHOLE tile in batches of FS_B lines; per line they copy the one contiguous
+// run of FS_SEG samples that the tile's points can touch (tile centre projected onto the line +- half diagonal +-
+// chord) into shared memory with coalesced loads, and every thread then evaluates the line exactly as fi_line
+// does, reading the samples from shared memory (a sample outside the staged run -- never for the sizes the bound
+// below is derived for -- is read from global memory, so the result does not depend on that bound).
+// The tile's angle range is a superset of each of its points' ranges; the exact distance test of fi_line decides.
+// ------------------------------------------------------------------------------------------
+constexpr int FS_B = 32;    // lines per batch
+constexpr int FS_SEG = 32;  // staged samples per line
+constexpr int FS_TX = 16, FS_TY = 8;  // the tile of grid points (128 threads)
+
+__device__ __forceinline__ void fi_line_s(const float2 *__restrict__ g, const float2 (*sm)[FS_SEG], int r0,
+                                          float theta, float2 (&acc)[FI_SC], float px, float py, float radius_2,
+                                          int proj, int z0, int nzc, float coeff0, float coeff1, int n, int nproj) {
+  float st, ct;
+  __sincosf(theta, &st, &ct);
+  const float pr = 0.5f, pr2 = 0.25f;
+  const float vx = pr * ct, vy = pr * st;
+  const float dot = vx * px + vy * py;
+  const float mx = dot * vx / pr2, my = dot * vy / pr2;
+  const float d2 = (mx - px) * (mx - px) + (my - py) * (my - py);
+  if (!(radius_2 >= d2)) return;
+  const float reach = __fsqrt_rn(radius_2 - d2);
+  int rmin, rmax;
+  if (fabsf(vx) > fabsf(vy)) {
+    rmin = n / 2 - 1 + (int)floorf((mx - reach * vx / pr) / (2.f * vx / n));
+    rmax = n / 2 + 1 + (int)floorf((mx + reach * vx / pr) / (2.f * vx / n));
+  } else {
+    rmin = n / 2 - 1 + (int)floorf((my - reach * vy / pr) / (2.f * vy / n));
+    rmax = n / 2 + 1 + (int)floorf((my + reach * vy / pr) / (2.f * vy / n));
+  }
+  if (rmin > rmax) { const int t = rmax; rmax = rmin; rmin = t; }
+  rmin = min(max(rmin, 0), n - 1);
+  rmax = min(max(rmax, 0), n - 1);
+  const size_t plane = (size_t)n * nproj;
+  const float2 *row = g + (size_t)proj * n + (size_t)z0 * plane;
+  for (int ri = rmin; ri < rmax; ++ri) {  // exclusive upper bound, like the reference
+    float x0 = (ri - n / 2) / (float)n * ct;
+    float y0 = (ri - n / 2) / (float)n * st;
+    if (x0 >= 0.5f) x0 = 0.5f - 1e-5;
+    if (y0 >= 0.5f) y0 = 0.5f - 1e-5;
+    const float w0 = px - x0, w1 = py - y0;
+    const float w = coeff0 * __expf(coeff1 * (w0 * w0 + w1 * w1));
+    const unsigned k = (unsigned)(ri - r0);
+    if (k < (unsigned)FS_SEG) {
+#pragma unroll
+      for (int s = 0; s < FI_SC; ++s) {
+        const float2 v = sm[s][k];
+        acc[s].x += v.x * w;
+        acc[s].y += v.y * w;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < FI_SC; ++s) {
+        if (s < nzc) {
+          const float2 v = __ldg(row + (size_t)s * plane + ri);
+          acc[s].x += v.x * w;
+          acc[s].y += v.y * w;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_fi_gather_s(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta,
+                  const float *__restrict__ sth, const int *__restrict__ sidx, int m, float mu, int n, int nproj,
+                  int nz2, int center_size) {
+  __shared__ float2 sm[FS_B][FI_SC][FS_SEG];  // 32 KB
+  __shared__ int s_proj[FS_B], s_r0[FS_B];
+  __shared__ float s_theta[FS_B];
+  __shared__ float2 s_cs[FS_B];  // (cos, sin) of the line: the cheap rejection test below
+  const int n2 = 2 * n;
+  const int c0 = max(0, n - center_size / 2);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  // the CTA's tile: FS_TX x FS_TY grid points (a warp = two rows of 16)
+  const int lx = blockIdx.x * FS_TX + (tid & (FS_TX - 1)), ly = blockIdx.y * FS_TY + tid / FS_TX;
+  const int tx = c0 + lx, ty = c0 + ly;
+  const int z0 = blockIdx.z * FI_SC;
+  const bool on = lx < center_size && ly < center_size && tx < n2 && ty < n2;
+  const int nzc = min(FI_SC, nz2 - z0);
+  const float coeff0 = FI_PI / mu;
+  const float coeff1 = -FI_PI * FI_PI / mu;
+  const int fs2 = n2 * n2;
+  const float radius_2 = 2.f * ((float)m + 0.5f) * ((float)m + 0.5f) / fs2;
+  const float radius = __fsqrt_rn(radius_2);
+  const float px = (float)(tx - n) / (float)n2, py = (float)(n - ty) / (float)n2;
+
+  float2 acc[FI_SC];
+#pragma unroll
+  for (int s = 0; s < FI_SC; ++s) acc[s] = make_float2(0.f, 0.f);
+
+  // the tile: centre and half diagonal (normalised frequency units), the same for every thread of the CTA
+  const float pcx = ((float)(c0 + (int)blockIdx.x * FS_TX - n) + 0.5f * (FS_TX - 1)) / (float)n2;
+  const float pcy = ((float)(n - (c0 + (int)blockIdx.y * FS_TY)) - 0.5f * (FS_TY - 1)) / (float)n2;
+  // half diagonal of the tile in cells, with a margin
+  const float hd = (0.5f * sqrtf((float)((FS_TX - 1) * (FS_TX - 1) + (FS_TY - 1) * (FS_TY - 1))) + 0.6f) / (float)n2;
+  const float lenc = __fsqrt_rn(pcx * pcx + pcy * pcy);
+  const float reachc = radius + hd;  // a line farther than this from the tile centre touches none of its points
+  const size_t plane = (size_t)n * nproj;
+
+  // sorted-index ranges of the lines that may touch the tile (at most 3 pieces, in ascending order, deduplicated)
+  int rlo[3], rhi[3], nr = 0;
+  if (reachc >= lenc) {
+    rlo[0] = 0; rhi[0] = nproj; nr = 1;
+  } else {
+    const float delta = asinf(fminf(1.f, reachc / lenc)) + 2e-3f;
+    const float phi = atan2f(pcy, pcx);
+    const float tmin = __ldg(sth), tmax = __ldg(sth + nproj - 1);
+    const int kmin = (int)ceilf((tmin - phi - delta) / FI_PI);
+    const int kmax = (int)floorf((tmax - phi + delta) / FI_PI);
+    int done = 0;
+    for (int k = kmin; k <= kmax && nr < 3; ++k) {
+      const float a = phi - delta + k * FI_PI, b = phi + delta + k * FI_PI;
+      int lo = lower_bound_f(sth, nproj, a);
+      const int hi = upper_bound_f(sth, nproj, b);
+      lo = max(lo, done);
+      if (hi > lo) { rlo[nr] = lo; rhi[nr] = hi; ++nr; }
+      done = max(done, hi);
+    }
+    if (kmax - kmin + 1 > 3) { rlo[0] = 0; rhi[0] = nproj; nr = 1; }  // (angles spanning more than 3 pi: take all)
+  }
+
+  for (int piece = 0; piece < nr; ++piece) {
+    for (int j0 = rlo[piece]; j0 < rhi[piece]; j0 += FS_B) {
+      const int nb = min(FS_B, rhi[piece] - j0);
+      // ---- stage: thread b < nb sets up line b of the batch, then everybody copies
+      if (tid < nb) {
+        const int proj = __ldg(sidx + j0 + tid);
+        const float th = __ldg(theta + proj);
+        float st, ct;
+        __sincosf(th, &st, &ct);
+        const float tc = pcx * ct + pcy * st;  // tile centre along the line
+        // first sample any point of the tile can ask for: (tc - hd - radius) n + n/2, minus the kernel's own margins
+        int r0 = (int)floorf((tc - hd - radius) * (float)n) + n / 2 - 3;
+        r0 = max(0, min(r0, n - FS_SEG));
+        s_proj[tid] = proj; s_theta[tid] = th; s_r0[tid] = r0; s_cs[tid] = make_float2(ct, st);
+      }
+      __syncthreads();
+      {
+        const int k = tid & (FS_SEG - 1), s = tid >> 5;  // 128 threads = FS_SEG samples x FI_SC slices
+#pragma unroll 8
+        for (int b = 0; b < nb; ++b) {
+          float2 v = make_float2(0.f, 0.f);
+          const int ri = s_r0[b] + k;
+          if (s < nzc && ri < n) v = __ldg(g + (size_t)(z0 + s) * plane + (size_t)s_proj[b] * n + ri);
+          sm[b][s][k] = v;
+        }
+      }
+      __syncthreads();
+      // ---- accumulate
+      if (on) {
+        for (int b = 0; b < nb; ++b) {
+          // cheap rejection with a margin (distance of the point from the line through the origin); fi_line_s
+          // applies the reference's own test to what is left
+          const float2 cs = s_cs[b];
+          const float dq = py * cs.x - px * cs.y;
+          if (dq * dq > radius_2 * 1.01f + 1e-12f) continue;
+          fi_line_s(g, sm[b], s_r0[b], s_theta[b], acc, px, py, radius_2, s_proj[b], z0, nzc, coeff0, coeff1, n, nproj);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!on) return;
+  // the (-1)^(x+y) of the centred inverse 2-D FFT (c2dfftshift, :588-609) is applied on the way out
+  const float sg = ((tx ^ ty) & 1) ? -1.f : 1.f;
+  const size_t o = (size_t)ty * n2 + tx;
+#pragma unroll
+  for (int s = 0; s < FI_SC; ++s)
+    if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = make_float2(acc[s].x * sg, acc[s].y * sg);
+}
+
 // The scatter ("gather_kernel" / "gather_kernel_partial", fft_us_kernels.cu:44-109) of the non-default branches
 // (methodsDIR_CuPy.py:761-779, 818-835: center_size < 192, or a centre square smaller than the grid): every polar
 // sample spreads its (2m+1)^2 Gaussian footprint onto the grid with atomic adds; PARTIAL skips the targets inside
@@ -283,10 +462,25 @@ extern "C" int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz
   return check_launch("k_fi_scale_sign");
 }
 
+// test hook: 1 = k_fi_gather (every thread loads its own samples), 0 = the measured best
+static int g_fi_gather_mode = 0;
+extern "C" int tmb_fi_set_gather(int mode) {
+  const int old = g_fi_gather_mode;
+  g_fi_gather_mode = (mode == 1 || mode == 2) ? mode : 0;
+  return old;
+}
+
 static int fi_gather_launch(const float *datac, float *fde, const float *theta, const float *sorted_theta,
                             const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, int center_size,
                             void *stream) {
   dim3 block(32, 4), grid((center_size + 31) / 32, (center_size + 3) / 4, (nz2 + FI_SC - 1) / FI_SC);
+  if (g_fi_gather_mode == 2) {
+    const dim3 sgrid((center_size + FS_TX - 1) / FS_TX, (center_size + FS_TY - 1) / FS_TY, (nz2 + FI_SC - 1) / FI_SC);
+    k_fi_gather_s<<<sgrid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
+                                                            reinterpret_cast<float2 *>(fde), theta, sorted_theta,
+                                                            sorted_idx, m, mu, n, nproj, nz2, center_size);
+    return check_launch("k_fi_gather_s");
+  }
   k_fi_gather<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
                                                         reinterpret_cast<float2 *>(fde), theta, sorted_theta,
                                                         sorted_idx, m, mu, n, nproj, nz2, center_size);
