@@ -153,3 +153,24 @@ def test_untimed_variants_of_the_fused_kernel(shape, mode):
     for a, b in zip(res[mode], res[3]):
         assert np.isfinite(a).all() and rel_max(a, b) < 2e-6
 
+
+
+@pytest.mark.parametrize("shape", [(9, 21, 244), (66, 37, 364), (40, 130, 8)])
+@pytest.mark.parametrize("half", [False, True])
+def test_rof_fast_normalisation_stays_on_the_exact_path(shape, half):
+    """k_rof_tv3d_w's default arithmetic (nom * MUFU.RSQ: raw approximation, <= 2^-22.9 relative) against the round-1
+    path behind hook 3 (correctly rounded square root + IEEE division, the reference's own sequence): after 30
+    iterations at the benchmark's parameters the two agree to 5e-7 of the volume's range."""
+    from tomobar_b200._lib import lib
+    from tomobar_b200.regularisersCuPy import ROF_TV_cupy
+
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    v = torch.randn(shape, device="cuda", generator=g) * 0.02
+    fast = ROF_TV_cupy(v, 3e-4, 30, 1e-3, 0, half)
+    old = lib.tmb_tv_set_simple_kernels(3)
+    try:
+        exact = ROF_TV_cupy(v, 3e-4, 30, 1e-3, 0, half)
+    finally:
+        lib.tmb_tv_set_simple_kernels(old)
+    assert torch.isfinite(fast).all()
+    assert (fast - exact).abs().max().item() <= 5e-7 * exact.abs().max().item()
