@@ -489,9 +489,10 @@ def run_direct(args, cfg):
                                                              ptr(sorted_idx), m, float(np.float32(mu)), n, na, nz2, st),
                                            "tmb_fi_gather"), 3)
         bytes_k = 8.0 * nz2 * na * n + 8.0 * nz2 * 4 * n * n  # polar samples read once, grid written once
-        kname = ("k_fi_gather (USFFT gather onto the 2n x 2n grid: latency / SFU-bound, the grid write is its "
+        kname = ("k_fi_gather_w (USFFT gather onto the 2n x 2n grid, a warp walks the polar lines of its patch in lock "
+                 "step: issue-bound, the grid write is its "
                  "algorithmic HBM traffic)")
-        traffic = traffic_of("k_fi_gather", int(nz2) * 4 * n * n)
+        traffic = traffic_of("k_fi_gather_w", int(nz2) * 4 * n * n)
         del datac, fde
         launches = 8  # pad, filter product, pack, scale-sign, gather, unpad (+ cuFFT's own kernels, not counted)
     else:

@@ -233,9 +233,12 @@ int tmb_normalise(const void *data, int data_is_u16, const float *flat_mean, con
  *                         -> recon[unpad_z][R][R]                                         (unpadding_mul_phi :611-657) */
 int tmb_fi_pack(const float *tmp_p, float *datac, int n, int nproj, int nz2, void *stream);
 int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
-/* test hook: 1 = k_fi_gather (every thread loads its own samples), 2 = k_fi_gather_s (samples of a tile staged in
- * shared memory), 0 = the measured best.  Returns the old value. */
+/* test hook: 1 = k_fi_gather (every thread walks its own polar lines), 2 = k_fi_gather_s (samples of a tile staged in
+ * shared memory), 3 = k_fi_gather_w (a warp walks the lines of its 8 x 4 patch in lock step), 0 = the measured best (3).
+ * Returns the old value. */
 int tmb_fi_set_gather(int mode);
+/* test hook: complex slices per thread of k_fi_gather_w (2, 4, 8 or 16; 0 = the default).  Returns the old value. */
+int tmb_fi_set_slices_per_thread(int sc);
 int tmb_fi_gather(const float *datac, float *fde, const float *theta, const float *sorted_theta,
                   const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream);
 /* The non-default branches of FOURIER_INV (methodsDIR_CuPy.py:759-835, taken for the keyword center_size < 2n):

@@ -113,10 +113,11 @@ def test_fourier_inv_scatter_branches_vs_reference_kernels(scan, center_size):
 
 @pytest.mark.parametrize("n,na,nz,span,center", [(362, 241, 10, math.pi, None), (256, 180, 6, 2 * math.pi, None),
                                                   (200, 97, 4, math.pi, 224)])
-def test_tile_staged_gather_is_bit_identical(n, na, nz, span, center):
-    """k_fi_gather_s (hook 2: the polar samples of a 16 x 8 tile of grid points staged in shared memory, the tile's
-    angle range walked in batches) visits every (point, line, sample) of k_fi_gather (hook 1) in the same order:
-    the grids are bit-identical, on the whole grid and on a centre square."""
+def test_gather_variants_are_bit_identical(n, na, nz, span, center):
+    """k_fi_gather_w (the default: a warp walks the polar lines of its 8 x 4 patch of grid points in lock step) and
+    k_fi_gather_s (hook 2: the samples of a 16 x 8 tile staged in shared memory, the tile's angle range walked in
+    batches) visit every (point, line, sample) of k_fi_gather (hook 1: every thread walks its own lines) in the same
+    order: the grids are bit-identical, on the whole grid and on a centre square."""
     from tomobar_b200._lib import lib, check
     from tomobar_b200._tensors import ptr
 
@@ -131,7 +132,7 @@ def test_tile_staged_gather_is_bit_identical(n, na, nz, span, center):
     mu = -np.log(1e-4) / (2 * n * n)
     m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(1e-4) + (mu * n) * (mu * n) / 4)))
     out = {}
-    for mode in (1, 2):
+    for mode in (1, 2, 3, 0):
         fde = torch.zeros((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
         old = lib.tmb_fi_set_gather(mode)
         try:
@@ -144,5 +145,6 @@ def test_tile_staged_gather_is_bit_identical(n, na, nz, span, center):
         finally:
             lib.tmb_fi_set_gather(old)
         out[mode] = torch.view_as_real(fde)
-    assert torch.isfinite(out[2]).all() and out[1].abs().max() > 0
-    assert torch.equal(out[1], out[2])
+    assert torch.isfinite(out[3]).all() and out[1].abs().max() > 0
+    for mode in (2, 3, 0):
+        assert torch.equal(out[1], out[mode])

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),
     "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
     "tmb_fi_set_gather": (_i, [_i]),
+    "tmb_fi_set_slices_per_thread": (_i, [_i]),
     "tmb_fi_gather": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _vp]),
     "tmb_fi_gather_center": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
     "tmb_fi_scatter": (_i, [_fp, _fp, _fp, _i, _f, _i, _i, _i, _i, _vp]),

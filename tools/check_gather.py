@@ -23,8 +23,9 @@ for n, na, nz, span in ((2048, 2000, 128, np.pi), (362, 241, 10, np.pi), (256, 1
     m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(1e-4) + (mu * n) * (mu * n) / 4)))
     fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
     ref = None
-    for mode in (1, 2):
-        lib.tmb_fi_set_gather(mode)
+    for mode in (1, 2, 3, 38, 316, 0):  # 3x: k_fi_gather_w with x complex slices per thread
+        lib.tmb_fi_set_gather(3 if mode > 3 else mode)
+        lib.tmb_fi_set_slices_per_thread((mode - 300 if mode > 300 else mode - 30) if mode > 3 else (4 if mode == 3 else 0))
         fn = lambda: check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
                                              float(np.float32(mu)), n, na, nz2, st), "g")
         fde.fill_(float("nan"))
@@ -41,5 +42,6 @@ for n, na, nz, span in ((2048, 2000, 128, np.pi), (362, 241, 10, np.pi), (256, 1
               f"{(d.norm() / ref.norm()).item():.2e}  max {d.abs().max().item():.2e} (|ref| max {ref.abs().max().item():.2e}) "
               f"finite={bool(torch.isfinite(r).all())}", flush=True)
     lib.tmb_fi_set_gather(0)
+    lib.tmb_fi_set_slices_per_thread(0)
     del datac, fde, ref, r, d
     torch.cuda.empty_cache()

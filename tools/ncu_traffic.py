@@ -16,7 +16,7 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 out = []
 for r in rows[2:]:
     name = r[idx["Kernel Name"]]
-    kern = next((k for k in ("k_pd_tv3d_f2s", "k_pd_tv3d_f2", "k_pd_tv3d_w", "k_rof_tv3d_w", "k_fi_gather") if k in name), None)
+    kern = next((k for k in ("k_pd_tv3d_f2s", "k_pd_tv3d_f2", "k_pd_tv3d_w", "k_rof_tv3d_w", "k_fi_gather_w", "k_fi_gather") if k in name), None)
     if kern is None:
         continue
     tot = 0.0
