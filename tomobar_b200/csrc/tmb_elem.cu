@@ -147,6 +147,23 @@ __global__ void k_edge_pad(const float *__restrict__ in, float *__restrict__ out
   }
 }
 
+// the same with 128-bit stores (wout % 4 == 0, 16-byte aligned out): a thread writes four consecutive outputs of a
+// row; the output is 4 x the input for FOURIER_INV's oversampled detector and mostly replicated edge values, so the
+// kernel is a store stream (round 2: 5.1 -> ~2 ms per call at config 4; the scalar version above divided a 64-bit
+// index per element)
+__global__ void k_edge_pad4(const float *__restrict__ in, float4 *__restrict__ out, size_t rows, int w, int wout4,
+                            int pad_left) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;  // which float4 of the row
+  if (q >= wout4) return;
+  const int j = 4 * q - pad_left;
+  const int i0 = min(max(j, 0), w - 1), i1 = min(max(j + 1, 0), w - 1), i2 = min(max(j + 2, 0), w - 1),
+            i3 = min(max(j + 3, 0), w - 1);
+  for (size_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float *row = in + r * (size_t)w;
+    out[r * (size_t)wout4 + q] = make_float4(__ldg(row + i0), __ldg(row + i1), __ldg(row + i2), __ldg(row + i3));
+  }
+}
+
 // circular mask (supp/suppTools.py:364-396)
 __global__ void k_mask(float *__restrict__ vol, int nz, int n, double limit) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +291,12 @@ extern "C" int tmb_normalise(const void *data, int data_is_u16, const float *fla
 extern "C" int tmb_edge_pad(const float *in, float *out, size_t rows, int w, int wout, int pad_left, void *stream) {
   TMB_REQUIRE(in && out && in != out && w >= 1 && wout >= w && pad_left >= 0 && pad_left + w <= wout,
               "tmb_edge_pad: bad argument");
+  if (wout % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    const int wout4 = wout / 4;
+    const dim3 grid((wout4 + 255) / 256, (unsigned)(rows < 16384 ? rows : 16384));
+    k_edge_pad4<<<grid, 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float4 *>(out), rows, w, wout4, pad_left);
+    return check_launch("k_edge_pad4");
+  }
   k_edge_pad<<<el_blocks(rows * (size_t)wout), EL_THREADS, 0, (cudaStream_t)stream>>>(in, out, rows, w, wout, pad_left);
   return check_launch("k_edge_pad");
 }
