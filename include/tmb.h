@@ -232,6 +232,11 @@ int tmb_normalise(const void *data, int data_is_u16, const float *flat_mean, con
  *   tmb_fi_unpad        : (-1)^(x+y) of the second c2dfftshift (:888-896, fused), crop, de-apodise, unpack re/im
  *                         -> recon[unpad_z][R][R]                                         (unpadding_mul_phi :611-657) */
 int tmb_fi_pack(const float *tmp_p, float *datac, int n, int nproj, int nz2, void *stream);
+/* tmb_fi_pack reading rows of pitch row_pitch (floats) inside slices of pitch slice_pitch: packs a chunk of slices straight
+ * out of the oversampled filter output (`in` points at the first kept detector sample), so that the crop of
+ * methodsDIR_CuPy.py:541-545 and the pack are one pass */
+int tmb_fi_pack_rows(const float *in, size_t row_pitch, size_t slice_pitch, float *datac, int n, int nproj, int nz2,
+                     void *stream);
 int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
 /* test hook: 1 = k_fi_gather (every thread walks its own polar lines), 2 = k_fi_gather_s (samples of a tile staged in
  * shared memory), 3 = k_fi_gather_w (a warp walks the lines of its 8 x 4 patch in lock step), 0 = the measured best (3).

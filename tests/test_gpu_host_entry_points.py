@@ -83,3 +83,18 @@ def test_two_geometries_on_two_streams(oracle):
     for i in range(2):
         for r in got[i]:
             assert torch.equal(r, want[i])
+
+
+@pytest.mark.parametrize("shape,pad_left,width_out", [((3, 7, 64), 32, 128), ((2, 5, 100), 6, 112), ((4, 3, 37), 5, 51),
+                                                      ((1, 9, 48), 0, 48), ((2, 4, 33), 7, 44), ((1, 1, 1), 3, 8)])
+def test_edge_pad_kernels(shape, pad_left, width_out):
+    """supp.suppTools.edge_pad (suppTools.py:425-459 of the reference: np.pad(..., mode='edge') of the detector axis)
+    through both kernels: 128-bit stores when the output rows are whole float4s, the scalar kernel otherwise."""
+    from tomobar_b200.supp.suppTools import edge_pad
+
+    g = torch.Generator(device="cuda").manual_seed(width_out)
+    x = torch.randn(shape, device="cuda", generator=g)
+    y = edge_pad(x, pad_left, width_out)
+    ref = np.pad(x.cpu().numpy(), ((0, 0), (0, 0), (pad_left, width_out - pad_left - shape[-1])), mode="edge")
+    assert y.shape == ref.shape
+    np.testing.assert_array_equal(y.cpu().numpy(), ref)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "tmb_circular_mask": (_i, [_fp, _i, _i, _f, _vp]),
     "tmb_normalise": (_i, [_vp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
     "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),
+    "tmb_fi_pack_rows": (_i, [_fp, _sz, _sz, _fp, _i, _i, _i, _vp]),
     "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
     "tmb_fi_set_gather": (_i, [_i]),
     "tmb_fi_set_slices_per_thread": (_i, [_i]),

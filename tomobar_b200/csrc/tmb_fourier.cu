@@ -37,6 +37,19 @@ __global__ void k_fi_pack(const float *__restrict__ in, float2 *__restrict__ out
   out[tz * plane + i] = make_float2(in[(2 * (size_t)tz) * plane + i] * sgn, in[(2 * (size_t)tz + 1) * plane + i] * sgn);
 }
 
+// the same from rows of pitch `row_pitch` floats inside slices of pitch `slice_pitch` floats: packs straight out of
+// the oversampled filter output (crop + pack in one pass; the filtered projections are never materialised)
+__global__ void k_fi_pack_rows(const float *__restrict__ in, size_t row_pitch, size_t slice_pitch,
+                               float2 *__restrict__ out, int n, int nproj, int nz2) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ty = blockIdx.y * blockDim.y + threadIdx.y;
+  const int tz = blockIdx.z;
+  if (tx >= n || ty >= nproj || tz >= nz2) return;
+  const float sgn = (tx & 1) ? 1.f : -1.f;
+  const float *a = in + (2 * (size_t)tz) * slice_pitch + (size_t)ty * row_pitch + tx;
+  out[((size_t)tz * nproj + ty) * n + tx] = make_float2(a[0] * sgn, a[slice_pitch] * sgn);
+}
+
 __global__ void k_fi_scale_sign(float2 *__restrict__ d, float c, int n, size_t rows) {
   const int tx = blockIdx.x * blockDim.x + threadIdx.x;
   if (tx >= n) return;
@@ -571,6 +584,16 @@ extern "C" int tmb_fi_pack(const float *in, float *datac, int n, int nproj, int 
   dim3 block(32, 8), grid((n + 31) / 32, (nproj + 7) / 8, nz2);
   k_fi_pack<<<grid, block, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float2 *>(datac), n, nproj, nz2);
   return check_launch("k_fi_pack");
+}
+
+extern "C" int tmb_fi_pack_rows(const float *in, size_t row_pitch, size_t slice_pitch, float *datac, int n, int nproj,
+                                int nz2, void *stream) {
+  TMB_REQUIRE(in && datac && n > 0 && nproj > 0 && nz2 > 0 && row_pitch >= (size_t)n && slice_pitch >= row_pitch * nproj,
+              "tmb_fi_pack_rows: bad argument");
+  dim3 block(32, 8), grid((n + 31) / 32, (nproj + 7) / 8, nz2);
+  k_fi_pack_rows<<<grid, block, 0, (cudaStream_t)stream>>>(in, row_pitch, slice_pitch, reinterpret_cast<float2 *>(datac), n,
+                                                           nproj, nz2);
+  return check_launch("k_fi_pack_rows");
 }
 
 extern "C" int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream) {

@@ -204,13 +204,12 @@ class RecToolsDIRCuPy:
 
         with torch.cuda.device(dev):
             # STEP 0: filtering on an oversampled detector with a half-pixel phase ramp (:449-545)
-            tmp_p = self._fourier_filter(data, data_n, n, power_of_2_oversampling, oversampling_level,
-                                         filter_type, cutoff_freq)
-            del data
-            # STEP 1: pair slices into complex slices, 1-D FFT along the detector (:645-683, :725-754)
+            # ... and STEP 1a: slices paired into complex slices (:645-683), packed chunk by chunk out of the filter output
             datac = torch.empty((nz2, nproj, n), dtype=torch.complex64, device=dev)
-            check(lib.tmb_fi_pack(ptr(tmp_p), ptr(datac), n, nproj, nz2, st), "tmb_fi_pack")
-            del tmp_p
+            self._fourier_filter(data, data_n, n, power_of_2_oversampling, oversampling_level, filter_type, cutoff_freq,
+                                 pack_into=datac)
+            del data
+            # STEP 1b: 1-D FFT along the detector (:725-754)
             datac = torch.fft.fft(datac, dim=-1)
             check(lib.tmb_fi_scale_sign(ptr(datac), float(np.float32(4 / n)), n, nproj, nz2, st), "tmb_fi_scale_sign")
             m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
@@ -326,7 +325,7 @@ class RecToolsDIRCuPy:
                 over = 2 ** math.ceil(math.log2(width))
         else:
             over = max(int(oversampling_level * raw_width), width)
-        tmp_p = nz * nproj * width * 4
+        tmp_p = nz * nproj * width * 4  # (= the bytes of the complex slice pairs the chunks are packed into)
         stack.malloc(tmp_p)
         per = min(nz, max(1, (1 << 27) // (nproj * over)))
         rows_real, rows_cplx = per * nproj * over * 4, per * nproj * (over // 2 + 1) * 8
@@ -345,9 +344,8 @@ class RecToolsDIRCuPy:
         from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
 
         stack = DeviceMemStack.instance()
-        datac = nz2 * nproj * n * 8
-        stack.malloc(datac)
-        stack.free(tmp_p)
+        datac = nz2 * nproj * n * 8                    # == tmp_p: the filter stage packed its chunks into it
+        assert datac == tmp_p
         stack.malloc(datac), stack.malloc(datac)      # FFT output + work area
         stack.free(datac), stack.free(datac)
         return datac, nz2 * (2 * n) * (2 * n) * 8
@@ -389,9 +387,13 @@ class RecToolsDIRCuPy:
         return recon_shape
 
     def _fourier_filter(self, data, raw_width, width, power_of_2_oversampling, oversampling_level, filter_type,
-                        cutoff_freq) -> torch.Tensor:
+                        cutoff_freq, pack_into=None):
         """rfft -> analytic filter with the rotation-axis phase ramp -> irfft on an edge-padded,
-        oversampled detector; cropped to ``width`` (methodsDIR_CuPy.py:449-545)."""
+        oversampled detector; cropped to ``width`` (methodsDIR_CuPy.py:449-545).
+
+        ``pack_into`` (the complex slice pairs ``datac[nz/2][nproj][width]`` of FOURIER_INV's next step): every chunk
+        of slices is cropped AND packed (r2c_c1dfftshift, fft_us_kernels.cu:529-557) straight out of the oversampled
+        ``irfft`` output -- the filtered projections are never written out as an array of their own.  Returns None then."""
         if power_of_2_oversampling:
             over = 2 ** math.ceil(math.log2(raw_width * 3))
             if width > over:
@@ -407,11 +409,22 @@ class RecToolsDIRCuPy:
         t = torch.fft.rfftfreq(over, device=dev).to(torch.float32)
         w = wfilter * torch.exp((-2 * np.pi * 1j * rotation_axis) * t.to(torch.complex64))
         nz, nproj, _ = data.shape
-        out = torch.empty((nz, nproj, width), dtype=torch.float32, device=dev)
         # slice chunks bound the oversampled temporaries (the reference chunks for the same reason)
         per = max(1, (1 << 27) // (nproj * over))
+        if pack_into is not None and per > 1:
+            per -= per % 2  # whole slice pairs per chunk
+        fused = pack_into is not None and per % 2 == 0 and nz % 2 == 0
+        out = None if fused else torch.empty((nz, nproj, width), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
         for z0 in range(0, nz, per):
             tmp = edge_pad(data[z0:z0 + per], padding_m, raw_width + 2 * padding_m)
             tmp = torch.fft.irfft(w * torch.fft.rfft(tmp, dim=2), n=over, dim=2)
-            out[z0:z0 + per] = tmp[:, :, unpad_m:unpad_p]
+            if fused:
+                check(lib.tmb_fi_pack_rows(ptr(tmp) + 4 * unpad_m, over, nproj * over, ptr(pack_into[z0 // 2:]), width, nproj,
+                                           tmp.shape[0] // 2, st), "tmb_fi_pack_rows")
+            else:
+                out[z0:z0 + per] = tmp[:, :, unpad_m:unpad_p]
+        if pack_into is not None and not fused:
+            check(lib.tmb_fi_pack(ptr(out), ptr(pack_into), width, nproj, nz // 2, st), "tmb_fi_pack")
+            return None
         return out
