@@ -412,9 +412,12 @@ __global__ void __launch_bounds__(128)
 // order as k_fi_gather: bit-identical grids.
 // ------------------------------------------------------------------------------------------
 constexpr int FW_PX = 8, FW_PY = 4;  // the patch of a warp
+#ifndef FW_MINB
+#define FW_MINB 4  // CTAs per SM the register allocation aims at (5: 96 registers with spills, 56 instead of 50 ms at config 4)
+#endif
 
 template <int SC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, FW_MINB)
     k_fi_gather_w(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta,
                   const float *__restrict__ sth, const int *__restrict__ sidx, int m, float mu, int n, int nproj,
                   int nz2, int center_size) {
