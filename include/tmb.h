@@ -230,13 +230,21 @@ int tmb_normalise(const void *data, int data_is_u16, const float *flat_mean, con
  *                         (gather_kernel_center_angle_based_prune :193-319 + gather_kernel_center :468-527)
  *   tmb_fi_sign2d       : fde *= (-1)^(x+y)                                              (c2dfftshift :588-609)
  *   tmb_fi_unpad        : (-1)^(x+y) of the second c2dfftshift (:888-896, fused), crop, de-apodise, unpack re/im
- *                         -> recon[unpad_z][R][R]                                         (unpadding_mul_phi :611-657) */
+ *                         -> recon[unpad_z][R][R]; fde is multiplied by `scale` first (1, or 1 / (2n)^2 after an
+ *                         unnormalised inverse 2-D FFT)                                   (unpadding_mul_phi :611-657) */
 int tmb_fi_pack(const float *tmp_p, float *datac, int n, int nproj, int nz2, void *stream);
 /* tmb_fi_pack reading rows of pitch row_pitch (floats) inside slices of pitch slice_pitch: packs a chunk of slices straight
  * out of the oversampled filter output (`in` points at the first kept detector sample), so that the crop of
  * methodsDIR_CuPy.py:541-545 and the pack are one pass */
 int tmb_fi_pack_rows(const float *in, size_t row_pitch, size_t slice_pitch, float *datac, int n, int nproj, int nz2,
                      void *stream);
+/* FOURIER_INV filters slice PAIRS as complex rows (real impulse response: real and imaginary part are filtered
+ * independently; one c2c transform instead of an r2c / c2r pair per slice):
+ *   tmb_edge_pad_pair : in[2 nzc][rows][w] -> out[nzc][rows][wout] complex, (slice 2t, slice 2t+1) edge-padded like tmb_edge_pad
+ *   tmb_fi_crop_sign  : complex rows of pitch row_pitch (complex samples; `in` points at the first kept one) ->
+ *                       datac[rows][n] * (-1)^(x+1): the crop of :541-545 and r2c_c1dfftshift (:529-557) in one pass */
+int tmb_edge_pad_pair(const float *in, float *out, int nzc, size_t rows, int w, int wout, int pad_left, void *stream);
+int tmb_fi_crop_sign(const float *in, size_t row_pitch, float *datac, int n, size_t rows, void *stream);
 int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
 /* test hook: 1 = k_fi_gather (every thread walks its own polar lines), 2 = k_fi_gather_s (samples of a tile staged in
  * shared memory), 3 = k_fi_gather_w (a warp walks the lines of its 8 x 4 patch in lock step), 0 = the measured best (3).
@@ -258,7 +266,7 @@ int tmb_fi_gather_center(const float *datac, float *fde, const float *theta, con
 int tmb_fi_scatter(const float *datac, float *fde, const float *theta, int m, float mu, int center_size, int n,
                    int nproj, int nz2, void *stream);
 int tmb_fi_sign2d(float *fde, int n, int nz2, void *stream);
-int tmb_fi_unpad(float *recon, const float *fde, float mu, int nproj, int unpad_recon_p, int unpad_z,
+int tmb_fi_unpad(float *recon, const float *fde, float mu, float scale, int nproj, int unpad_recon_p, int unpad_z,
                  int unpad_recon_m, int n, int nz2, void *stream);
 
 /* ---- host-buffer entry points (what a non-CUDA caller binds; H2D/D2H inside) --------------- */

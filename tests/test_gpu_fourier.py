@@ -148,3 +148,58 @@ def test_gather_variants_are_bit_identical(n, na, nz, span, center):
     assert torch.isfinite(out[3]).all() and out[1].abs().max() > 0
     for mode in (2, 3, 0):
         assert torch.equal(out[1], out[mode])
+
+
+@pytest.mark.parametrize("case", [(16, 180, 160, 160, 0, 0.0), (6, 120, 97, 96, 0, 2.5), (4, 90, 130, 100, 3, -1.25),
+                                  (8, 64, 256, 256, 0, 0.0)])
+@pytest.mark.parametrize("filter_type", ["shepp", "hann"])
+@pytest.mark.parametrize("pow2", [True, False])
+def test_fourier_filter_slice_pairs_match_per_slice_filter(case, filter_type, pow2):
+    """STEP 0 of FOURIER_INV (methodsDIR_CuPy.py:449-545) on complex slice-pair rows (one c2c transform pair per slice
+    pair, two-sided filter with the real Nyquist bin irfft implies) against the rfft / irfft per slice: the filtered,
+    packed projections agree to fp32 FFT rounding, with a shifted rotation axis and without power-of-two oversampling."""
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+
+    nz, na, detX, obj, pad, cor = case
+    g = torch.Generator(device="cuda").manual_seed(na + detX)
+    d = torch.rand((nz, na, detX + detX % 2), device="cuda", generator=g)
+    angles = np.linspace(0, math.pi, na, endpoint=False).astype(np.float32)
+    T = RecToolsDIRCuPy(detX, pad, nz, cor, angles, obj, device_projector=0)
+    n = d.shape[-1] + 2 * pad
+    out = []
+    for pairs in (True, False):
+        T._FILTER_SLICE_PAIRS = pairs
+        datac = torch.empty((nz // 2, na, n), dtype=torch.complex64, device="cuda")
+        assert T._fourier_filter(d, d.shape[-1], n, pow2, 4, filter_type, 1.0, pack_into=datac) is None
+        out.append(torch.view_as_real(datac).cpu().numpy())
+    assert rel_l2(out[0], out[1]) < 2e-6, rel_l2(out[0], out[1])
+    assert rel_max(out[0], out[1]) < 2e-5, rel_max(out[0], out[1])
+
+
+@pytest.mark.parametrize("pairs", [True, False])
+def test_fourier_filter_8192_point_rows_vs_float64(pairs):
+    """STEP 0 at config 4's row length (2048 detector pixels oversampled to 8192) against a float64 rfft / irfft with
+    numpy's irfft semantics (imaginary part of the Nyquist bin ignored).  The phase ramp of a centred rotation axis makes
+    that bin purely imaginary; cuFFT's c2r used it at this size (7.7e-3 relative) until the bin was made real."""
+    from tomobar_b200.fourier import calc_filter
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+
+    n, nz, na = 2048, 4, 24
+    angles = np.linspace(0, math.pi, na, endpoint=False).astype(np.float32)
+    T = RecToolsDIRCuPy(n, 0, nz, 0.0, angles, n, device_projector=0)
+    T._FILTER_SLICE_PAIRS = pairs
+    g = torch.Generator(device="cuda").manual_seed(5)
+    d = torch.rand((nz, na, n), device="cuda", generator=g)
+    datac = torch.empty((nz // 2, na, n), dtype=torch.complex64, device="cuda")
+    T._fourier_filter(d, n, n, True, 4, "shepp", 1.0, pack_into=datac)
+    over = 8192
+    pm = over // 2 - n // 2
+    w64 = torch.as_tensor(calc_filter(over, "shepp", 1.0), device="cuda").double() * torch.exp(
+        (-2 * np.pi * 1j * 0.5) * torch.fft.rfftfreq(over, device="cuda").double())
+    torch.view_as_real(w64)[over // 2, 1] = 0.0
+    x = torch.nn.functional.pad(d.double(), (pm, over - pm - n), mode="replicate")
+    y = torch.fft.irfft(w64 * torch.fft.rfft(x, dim=2), n=over, dim=2)[:, :, pm:pm + n]
+    sgn = torch.where(torch.arange(n, device="cuda") % 2 == 1, 1.0, -1.0)
+    ref = torch.complex(y[0::2] * sgn, y[1::2] * sgn)
+    err = float((datac - ref).norm() / ref.norm())
+    assert err < 2e-6, err

@@ -156,7 +156,7 @@ def test_fbp2d_mask_and_agreement_with_the_sinc_fbp(scan):  # :144-169
 
 def test_fourier_inv_estimate_at_config4_within_5_percent():
     """BASELINE.json config 4 (2048^2 x 128, 2000 angles): the dry-run estimate against torch's measured peak
-    (measured on B200: 14.982 GB both; tools/check_estimator.py)."""
+    (tools/check_estimator.py)."""
     import torch
 
     from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy

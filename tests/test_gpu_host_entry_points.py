@@ -98,3 +98,30 @@ def test_edge_pad_kernels(shape, pad_left, width_out):
     ref = np.pad(x.cpu().numpy(), ((0, 0), (0, 0), (pad_left, width_out - pad_left - shape[-1])), mode="edge")
     assert y.shape == ref.shape
     np.testing.assert_array_equal(y.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shape,pad_left,width_out", [((4, 7, 64), 32, 128), ((2, 5, 100), 6, 112), ((6, 3, 37), 5, 52),
+                                                      ((2, 9, 48), 0, 48), ((2, 1, 1), 3, 8)])
+def test_edge_pad_pair_and_crop_sign(shape, pad_left, width_out):
+    """The two kernels either side of FOURIER_INV's complex slice-pair filter: tmb_edge_pad_pair (np.pad(mode='edge') of
+    slices 2t and 2t+1 into the real / imaginary part of one complex row) and tmb_fi_crop_sign (crop of
+    methodsDIR_CuPy.py:541-545 plus the (-1)^(x+1) of r2c_c1dfftshift, fft_us_kernels.cu:529-557).  Bit-exact."""
+    from tomobar_b200._lib import check, lib
+    from tomobar_b200._tensors import ptr
+
+    g = torch.Generator(device="cuda").manual_seed(width_out)
+    x = torch.randn(shape, device="cuda", generator=g)
+    nz, rows, w = shape
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.empty((nz // 2, rows, width_out), dtype=torch.complex64, device="cuda")
+    check(lib.tmb_edge_pad_pair(ptr(x), ptr(y), nz // 2, rows, w, width_out, pad_left, st), "tmb_edge_pad_pair")
+    ref = np.pad(x.cpu().numpy(), ((0, 0), (0, 0), (pad_left, width_out - pad_left - w)), mode="edge")
+    got = y.cpu().numpy()
+    np.testing.assert_array_equal(got.real, ref[0::2])
+    np.testing.assert_array_equal(got.imag, ref[1::2])
+    n = max(1, width_out // 2)
+    off = (width_out - n) // 2
+    z = torch.empty((nz // 2, rows, n), dtype=torch.complex64, device="cuda")
+    check(lib.tmb_fi_crop_sign(ptr(y) + 8 * off, width_out, ptr(z), n, (nz // 2) * rows, st), "tmb_fi_crop_sign")
+    sgn = np.where(np.arange(n) % 2 == 1, 1.0, -1.0).astype(np.float32)
+    np.testing.assert_array_equal(z.cpu().numpy(), got[:, :, off:off + n] * sgn)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "tmb_normalise": (_i, [_vp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
     "tmb_fi_pack": (_i, [_fp, _fp, _i, _i, _i, _vp]),
     "tmb_fi_pack_rows": (_i, [_fp, _sz, _sz, _fp, _i, _i, _i, _vp]),
+    "tmb_edge_pad_pair": (_i, [_fp, _fp, _i, _sz, _i, _i, _i, _vp]),
+    "tmb_fi_crop_sign": (_i, [_fp, _sz, _fp, _i, _sz, _vp]),
     "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
     "tmb_fi_set_gather": (_i, [_i]),
     "tmb_fi_set_slices_per_thread": (_i, [_i]),
@@ -68,7 +70,7 @@ SIGNATURES = {
     "tmb_fi_gather_center": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
     "tmb_fi_scatter": (_i, [_fp, _fp, _fp, _i, _f, _i, _i, _i, _i, _vp]),
     "tmb_fi_sign2d": (_i, [_fp, _i, _i, _vp]),
-    "tmb_fi_unpad": (_i, [_fp, _fp, _f, _i, _i, _i, _i, _i, _i, _vp]),
+    "tmb_fi_unpad": (_i, [_fp, _fp, _f, _f, _i, _i, _i, _i, _i, _i, _vp]),
     "tmb_fp3d_host": (_i, [_vp, _i, _fp, _fp]),
     "tmb_bp3d_host": (_i, [_vp, _i, _fp, _fp]),
 }

@@ -164,6 +164,24 @@ __global__ void k_edge_pad4(const float *__restrict__ in, float4 *__restrict__ o
   }
 }
 
+// edge padding of TWO real slices into one complex row: out[t][row][j] = (in[2t][row][c], in[2t+1][row][c]),
+// c = clamp(j - pad_left, 0, w - 1).  FOURIER_INV filters slice pairs as complex rows (one c2c transform instead of two
+// r2c / c2r: the filter has a real impulse response, so real and imaginary part are filtered independently), which is
+// also the pairing its gridding step needs.  A thread writes two complex samples (one 128-bit store).
+__global__ void k_edge_pad_pair(const float *__restrict__ in, float4 *__restrict__ out, size_t rows, size_t slice_elems,
+                                int nzc, int w, int wout2, int pad_left) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;  // which pair of output samples of the row
+  if (q >= wout2) return;
+  const int j = 2 * q - pad_left;
+  const int i0 = min(max(j, 0), w - 1), i1 = min(max(j + 1, 0), w - 1);
+  for (size_t r = blockIdx.y; r < rows * (size_t)nzc; r += gridDim.y) {
+    const size_t t = r / rows, row = r - t * rows;
+    const float *a = in + (2 * t) * slice_elems + row * (size_t)w;
+    const float *b = a + slice_elems;
+    out[r * (size_t)wout2 + q] = make_float4(__ldg(a + i0), __ldg(b + i0), __ldg(a + i1), __ldg(b + i1));
+  }
+}
+
 // circular mask (supp/suppTools.py:364-396)
 __global__ void k_mask(float *__restrict__ vol, int nz, int n, double limit) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,6 +304,19 @@ extern "C" int tmb_normalise(const void *data, int data_is_u16, const float *fla
     k_normalise<float><<<el_blocks(total), EL_THREADS, 0, (cudaStream_t)stream>>>(
         static_cast<const float *>(data), flat_mean, dark_mean, out, total, n1, n2, angle_axis, take_log);
   return check_launch("k_normalise");
+}
+
+extern "C" int tmb_edge_pad_pair(const float *in, float *out, int nzc, size_t rows, int w, int wout, int pad_left,
+                                 void *stream) {
+  TMB_REQUIRE(in && out && nzc >= 1 && rows >= 1 && w >= 1 && wout >= w && wout % 2 == 0 && pad_left >= 0 &&
+                  pad_left + w <= wout && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+              "tmb_edge_pad_pair: bad argument");
+  const int wout2 = wout / 2;
+  const size_t total = rows * (size_t)nzc;
+  const dim3 grid((wout2 + 255) / 256, (unsigned)(total < 16384 ? total : 16384));
+  k_edge_pad_pair<<<grid, 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float4 *>(out), rows, rows * (size_t)w, nzc, w,
+                                                          wout2, pad_left);
+  return check_launch("k_edge_pad_pair");
 }
 
 extern "C" int tmb_edge_pad(const float *in, float *out, size_t rows, int w, int wout, int pad_left, void *stream) {

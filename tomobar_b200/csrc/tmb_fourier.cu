@@ -50,6 +50,18 @@ __global__ void k_fi_pack_rows(const float *__restrict__ in, size_t row_pitch, s
   out[((size_t)tz * nproj + ty) * n + tx] = make_float2(a[0] * sgn, a[slice_pitch] * sgn);
 }
 
+// crop + sign from COMPLEX rows (the slice pairs were filtered as complex rows): out[t][row][x] = in[t][row][off + x] * (-1)^(x+1)
+__global__ void k_fi_crop_sign(const float2 *__restrict__ in, size_t row_pitch, float2 *__restrict__ out, int n,
+                               size_t rows) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tx >= n) return;
+  const float sgn = (tx & 1) ? 1.f : -1.f;
+  for (size_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float2 v = in[r * row_pitch + tx];
+    out[r * (size_t)n + tx] = make_float2(v.x * sgn, v.y * sgn);
+  }
+}
+
 __global__ void k_fi_scale_sign(float2 *__restrict__ d, float c, int n, size_t rows) {
   const int tx = blockIdx.x * blockDim.x + threadIdx.x;
   if (tx >= n) return;
@@ -425,7 +437,16 @@ __global__ void __launch_bounds__(128, FW_MINB)
   const int c0 = max(0, n - center_size / 2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // CTA = 4 patches side by side: 32 x 4 grid points
-  const int px0 = blockIdx.x * 32 + warp * FW_PX, py0 = blockIdx.y * FW_PY;
+#ifndef FW_LINEAR_ROWS  // (A/B builds: -DFW_LINEAR_ROWS, -DFW_NO_SKIP; profiles/fourier_chunks_r02.txt)
+  // rows of patches are taken from the centre of the grid outwards: a point at distance |p| from the centre is crossed by
+  // ~1/|p| of the lines (all of them at the centre), so the centre's CTAs run ~100 x longer than the average one and
+  // must not be among the last to start (16 complex slices per launch, 8 per thread: 15.5 -> 13.9 ms)
+  const int by = blockIdx.y;
+  const int yrow = (int)(gridDim.y >> 1) + ((by & 1) ? -((by >> 1) + 1) : (by >> 1));
+#else
+  const int yrow = blockIdx.y;
+#endif
+  const int px0 = blockIdx.x * 32 + warp * FW_PX, py0 = yrow * FW_PY;
   const int lx = px0 + (lane & (FW_PX - 1)), ly = py0 + lane / FW_PX;
   const int tx = c0 + lx, ty = c0 + ly;
   const int z0 = blockIdx.z * SC;
@@ -451,6 +472,13 @@ __global__ void __launch_bounds__(128, FW_MINB)
 
   // sorted-index ranges of the lines that may touch the patch (at most 3 pieces, ascending, deduplicated)
   int rlo0 = 0, rhi0 = 0, rlo1 = 0, rhi1 = 0, rlo2 = 0, rhi2 = 0;
+  // The polar samples end at |p| = 1/2 and fi_line clamps its sample range to the line: a patch whose nearest point
+  // lies farther out than the Gaussian's reach plus fi_line's two samples of slack (2/n; 4/n taken) receives nothing
+  // -- the corners of the grid, 21 % of it, store their zeros without looking for a line.
+#ifndef FW_NO_SKIP
+  if (lenc - hd > 0.5f + radius + 4.f / (float)n) {
+  } else
+#endif
   if (reachc >= lenc) {
     rhi0 = nproj;
   } else {
@@ -554,8 +582,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__ f, float mu, int nproj, int up,
-                           int unpad_z, int um, int n, int nz2) {
+// `scale` multiplies the grid values first: 1 when the inverse 2-D FFT was normalised, 1 / (2n)^2 when it was not (the
+// product is rounded where the normalisation pass would have rounded it: same bits)
+__global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__ f, float mu, float scale, int nproj,
+                           int up, int unpad_z, int um, int n, int nz2) {
   const int rxu = blockIdx.x * blockDim.x + threadIdx.x;
   const int ryu = blockIdx.y * blockDim.y + threadIdx.y;
   const int rz = blockIdx.z;
@@ -565,6 +595,8 @@ __global__ void k_fi_unpad(float *__restrict__ recon, const float2 *__restrict__
   const int rs = up - um;
   const size_t rs2 = (size_t)rs * rs;
   float2 v = f[(size_t)rz * n2 * n2 + (size_t)(n / 2 + ry) * n2 + (n / 2 + rx)];
+  v.x = __fmul_rn(v.x, scale);
+  v.y = __fmul_rn(v.y, scale);
   if (((n / 2 + ry) ^ (n / 2 + rx)) & 1) {  // the second c2dfftshift, fused
     v.x = -v.x;
     v.y = -v.y;
@@ -599,6 +631,14 @@ extern "C" int tmb_fi_pack_rows(const float *in, size_t row_pitch, size_t slice_
   return check_launch("k_fi_pack_rows");
 }
 
+extern "C" int tmb_fi_crop_sign(const float *in, size_t row_pitch, float *datac, int n, size_t rows, void *stream) {
+  TMB_REQUIRE(in && datac && n > 0 && rows > 0 && row_pitch >= (size_t)n, "tmb_fi_crop_sign: bad argument");
+  dim3 grid((n + 127) / 128, (unsigned)(rows < 8192 ? rows : 8192));
+  k_fi_crop_sign<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(in), row_pitch,
+                                                         reinterpret_cast<float2 *>(datac), n, rows);
+  return check_launch("k_fi_crop_sign");
+}
+
 extern "C" int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream) {
   TMB_REQUIRE(datac && n > 0 && nproj > 0 && nz2 > 0, "tmb_fi_scale_sign: bad argument");
   const size_t rows = (size_t)nproj * nz2;
@@ -630,9 +670,10 @@ static int fi_gather_launch(const float *datac, float *fde, const float *theta, 
   dim3 block(32, 4), grid((center_size + 31) / 32, (center_size + 3) / 4, (nz2 + FI_SC - 1) / FI_SC);
   if (g_fi_gather_mode == 3 || g_fi_gather_mode == 0) {
     // complex slices per thread: g_fi_sc (test hook) or the measured best
-    // (measured at 2048^2, 2000 angles, 64 complex slices: 4 -> 61.7, 8 -> 56.8, 16 -> 50.7 ms, 32 -> 232 ms (spills);
-    // at 5 slices 4 is best)
-    const int sc = g_fi_sc ? g_fi_sc : (nz2 >= 32 ? 16 : (nz2 >= 16 ? 8 : FW_SC_DEFAULT));
+    // (measured at 2048^2, 2000 angles, 64 complex slices: 4 -> 60.9, 8 -> 55.6, 16 -> 50.7 ... 64.8 ms depending on the
+    // box (the 128-register build of 16 is the only variant whose time moves between boxes), 32 -> 232 ms (spills);
+    // 16 complex slices, as FOURIER_INV launches it: 4 -> 15.3, 8 -> 13.9, 16 -> 18.3 ms; at 5 slices 4 is best)
+    const int sc = g_fi_sc ? g_fi_sc : (nz2 >= 16 ? 8 : FW_SC_DEFAULT);
     const dim3 wgrid((center_size + 31) / 32, (center_size + FW_PY - 1) / FW_PY, (nz2 + sc - 1) / sc);
 #define TMB_FW(SC_)                                                                                                  \
   k_fi_gather_w<SC_><<<wgrid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),               \
@@ -698,12 +739,12 @@ extern "C" int tmb_fi_sign2d(float *fde, int n, int nz2, void *stream) {
   return check_launch("k_fi_sign2d");
 }
 
-extern "C" int tmb_fi_unpad(float *recon, const float *fde, float mu, int nproj, int unpad_recon_p, int unpad_z,
-                            int unpad_recon_m, int n, int nz2, void *stream) {
+extern "C" int tmb_fi_unpad(float *recon, const float *fde, float mu, float scale, int nproj, int unpad_recon_p,
+                            int unpad_z, int unpad_recon_m, int n, int nz2, void *stream) {
   TMB_REQUIRE(recon && fde && n > 0 && nz2 > 0 && unpad_recon_p > unpad_recon_m, "tmb_fi_unpad: bad argument");
   const int rs = unpad_recon_p - unpad_recon_m;
   dim3 block(32, 8), grid((rs + 31) / 32, (rs + 7) / 8, nz2);
-  k_fi_unpad<<<grid, block, 0, (cudaStream_t)stream>>>(recon, reinterpret_cast<const float2 *>(fde), mu, nproj,
+  k_fi_unpad<<<grid, block, 0, (cudaStream_t)stream>>>(recon, reinterpret_cast<const float2 *>(fde), mu, scale, nproj,
                                                        unpad_recon_p, unpad_z, unpad_recon_m, n, nz2);
   return check_launch("k_fi_unpad");
 }

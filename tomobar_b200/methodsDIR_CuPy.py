@@ -111,6 +111,7 @@ class RecToolsDIRCuPy:
     # ------------------------------------------------------------------------------------------
     _FILTERS = ("none", "ramp", "shepp", "cosine", "cosine2", "hamming", "hann", "parzen")
     _CENTER_SIZE_MIN = 192  # methodsDIR_CuPy.py:23
+    _FILTER_SLICE_PAIRS = True  # FOURIER_INV filters slice pairs as complex rows (False: an r2c / c2r pair per slice)
 
     def FOURIER_INV(self, data, **kwargs) -> torch.Tensor:
         """Direct Fourier inversion on unequally spaced grids (USFFT gridding, Nikitin's
@@ -219,35 +220,41 @@ class RecToolsDIRCuPy:
             # and the rest scattered with atomic adds, or everything scattered (centre below _CENTER_SIZE_MIN)
             center_size = min(center_size, 2 * n)
             center_size -= center_size % 2
-            if center_size >= self._CENTER_SIZE_MIN and center_size == 2 * n:
-                fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
-                check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
-                                        float(np.float32(mu)), n, nproj, nz2, st), "tmb_fi_gather")
-            else:
-                # (the reference adds onto cp.empty memory in the partial branch, :661-670; zeros are what it means)
-                fde = torch.zeros((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
-                partial = center_size >= self._CENTER_SIZE_MIN
-                check(lib.tmb_fi_scatter(ptr(datac), ptr(fde), ptr(theta), m, float(np.float32(mu)),
-                                         center_size if partial else 0, n, nproj, nz2, st), "tmb_fi_scatter")
-                if partial:
-                    check(lib.tmb_fi_gather_center(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta),
-                                                   ptr(sorted_idx), m, float(np.float32(mu)), n, nproj, nz2,
-                                                   center_size, st), "tmb_fi_gather_center")
-            del datac
-            # STEP 3: centred 2-D inverse FFT (:851-896)
-            chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))  # bound cuFFT workspace
-            for s0 in range(0, nz2, chunk):
-                fde[s0:s0 + chunk] = torch.fft.ifft2(fde[s0:s0 + chunk], dim=(-2, -1))
-            # STEP 4: crop, de-apodise, unpack the slice pairs (:920-966)
+            whole = center_size >= self._CENTER_SIZE_MIN and center_size == 2 * n
+            partial = center_size >= self._CENTER_SIZE_MIN
+            # STEP 4's geometry: crop, de-apodise, unpack the slice pairs (:920-966)
             odd_recon = bool(recon_size % 2)
             unpad_z = nz - odd_vert
             um = (n - odd_horiz) // 2 - recon_size // 2
             up = (n - odd_horiz) // 2 + (recon_size + odd_recon) // 2
             rs = up - um
             recon_up = torch.empty((unpad_z, rs, rs), dtype=torch.float32, device=dev)
-            check(lib.tmb_fi_unpad(ptr(recon_up), ptr(fde), float(np.float32(mu)), nproj, up, unpad_z, um, n, nz2, st),
-                  "tmb_fi_unpad")
-            del fde
+            # STEPS 2-4 run chunk by chunk of complex slices (the slices are independent): the oversampled grid only
+            # ever exists for one chunk, the inverse 2-D FFT's output is read directly by the unpadding kernel (no
+            # copy back into a whole-volume grid) and its 1 / (2n)^2 is applied there (no normalisation pass)
+            chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))
+            mu32, inv_grid = float(np.float32(mu)), float(np.float32(1.0 / (4.0 * n * n)))
+            for s0 in range(0, nz2, chunk):
+                c = min(chunk, nz2 - s0)
+                dc = ptr(datac[s0:])
+                if whole:
+                    fde = torch.empty((c, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+                    check(lib.tmb_fi_gather(dc, ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m, mu32, n,
+                                            nproj, c, st), "tmb_fi_gather")
+                else:
+                    # (the reference adds onto cp.empty memory in the partial branch, :661-670; zeros are what it means)
+                    fde = torch.zeros((c, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
+                    check(lib.tmb_fi_scatter(dc, ptr(fde), ptr(theta), m, mu32, center_size if partial else 0, n, nproj,
+                                             c, st), "tmb_fi_scatter")
+                    if partial:
+                        check(lib.tmb_fi_gather_center(dc, ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
+                                                       mu32, n, nproj, c, center_size, st), "tmb_fi_gather_center")
+                # STEP 3: centred 2-D inverse FFT (:851-896), unnormalised
+                fde = torch.fft.ifft2(fde, dim=(-2, -1), norm="forward")
+                check(lib.tmb_fi_unpad(ptr(recon_up[2 * s0:]), ptr(fde), mu32, inv_grid, nproj, up, unpad_z - 2 * s0, um, n,
+                                       c, st), "tmb_fi_unpad")
+                del fde
+            del datac
         return check_kwargs(recon_up, **kwargs)
 
     def _fourier_inv_estimator(self, shape, **kwargs):
@@ -303,10 +310,14 @@ class RecToolsDIRCuPy:
         tmp_p = self._fbp_filtering_estimator(data_n, n, nproj, nz, power_of_2_oversampling, oversampling_level)
         if padded:
             stack.free(padded)                        # `del data`: only our padded copy goes away
-        datac, fde = self._setup_backprojection_input_estimator(n, nproj, nz2, tmp_p)
-        self._fft_and_interpolation_estimator(datac, fde)
-        self.ifft_gathered_projections_estimator(n, nz2)
-        recon_shape = self.unpad_reconstructed_data_estimator(fde, n, raw_nz, odd_horiz, recon_size)
+        datac, piece = self._setup_backprojection_input_estimator(n, nproj, nz2, tmp_p)
+        recon_shape, recon = self.unpad_reconstructed_data_estimator(n, raw_nz, odd_horiz, recon_size)
+        # STEPS 2-4 run per chunk of complex slices; every chunk has the same peak, so one is replayed
+        self._fft_and_interpolation_estimator(piece)
+        self.ifft_gathered_projections_estimator(piece)
+        stack.free(piece)                             # the chunk's transform, after its unpadding
+        stack.free(datac)
+        stack.free(recon)                             # (like the reference, the result itself is not kept on the stack)
         for b in (nproj * 4, nproj * 4, nproj * 4):
             stack.free(b)
         return recon_shape
@@ -327,8 +338,19 @@ class RecToolsDIRCuPy:
             over = max(int(oversampling_level * raw_width), width)
         tmp_p = nz * nproj * width * 4  # (= the bytes of the complex slice pairs the chunks are packed into)
         stack.malloc(tmp_p)
-        per = min(nz, max(1, (1 << 27) // (nproj * over)))
-        rows_real, rows_cplx = per * nproj * over * 4, per * nproj * (over // 2 + 1) * 8
+        per = max(1, (1 << 27) // (nproj * over))
+        if per > 1:
+            per -= per % 2  # whole slice pairs per chunk
+        rows_real, rows_cplx = min(per, nz) * nproj * over * 4, min(per, nz) * nproj * (over // 2 + 1) * 8
+        if per % 2 == 0 and nz % 2 == 0 and over % 2 == 0 and self._FILTER_SLICE_PAIRS:
+            # complex slice-pair rows: per / 2 * nproj * over * 8 bytes = rows_real
+            stack.malloc(over * 8)                             # the two-sided filter
+            stack.malloc(rows_real)                            # edge-padded slice pairs
+            stack.malloc(rows_real), stack.malloc(rows_real)   # their fft + its work area
+            stack.free(rows_real), stack.free(rows_real)       # (work area, then the padded rows)
+            stack.malloc(rows_real), stack.malloc(rows_real)   # inverse transform + its work area
+            stack.free(rows_real), stack.free(rows_real), stack.free(rows_real), stack.free(over * 8)
+            return tmp_p
         stack.malloc(rows_real)                            # edge-padded rows
         stack.malloc(rows_cplx), stack.malloc(rows_cplx)   # rfft output + its work area
         stack.free(rows_cplx)
@@ -340,7 +362,8 @@ class RecToolsDIRCuPy:
 
     def _setup_backprojection_input_estimator(self, n, nproj, nz2, tmp_p):
         """STEP 1 (reference twin :685-699): the complex slice pairs replace the filtered projections; their 1-D
-        FFT runs out of place (output + work area).  Returns the bytes of (datac, fde)."""
+        FFT runs out of place (output + work area).  Returns the bytes of datac and of one chunk of the oversampled
+        grid (STEPS 2-4 run chunk by chunk of complex slices)."""
         from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
 
         stack = DeviceMemStack.instance()
@@ -348,43 +371,37 @@ class RecToolsDIRCuPy:
         assert datac == tmp_p
         stack.malloc(datac), stack.malloc(datac)      # FFT output + work area
         stack.free(datac), stack.free(datac)
-        return datac, nz2 * (2 * n) * (2 * n) * 8
-
-    def _fft_and_interpolation_estimator(self, datac, fde):
-        """STEP 2 (reference twin :837-849): the oversampled Cartesian grid is allocated, gathered / scattered into,
-        and the polar samples are released.  No angle-range table here, whatever the centre size: the gather finds
-        its ranges on the fly."""
-        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
-
-        stack = DeviceMemStack.instance()
-        stack.malloc(fde)
-        stack.free(datac)
-
-    def ifft_gathered_projections_estimator(self, n, nz2):
-        """STEP 3 (reference twin :898-918): the inverse 2-D FFT runs in slice chunks (output chunk + work area)."""
-        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
-
-        stack = DeviceMemStack.instance()
         chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))
-        piece = chunk * (2 * n) * (2 * n) * 8
+        return datac, chunk * (2 * n) * (2 * n) * 8
+
+    def _fft_and_interpolation_estimator(self, piece):
+        """STEP 2 (reference twin :837-849): one chunk of the oversampled Cartesian grid is allocated and gathered /
+        scattered into.  No angle-range table here, whatever the centre size: the gather finds its ranges on the fly."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        DeviceMemStack.instance().malloc(piece)
+
+    def ifft_gathered_projections_estimator(self, piece):
+        """STEP 3 (reference twin :898-918): the chunk's inverse 2-D FFT runs out of place (output + work area), then
+        its input is released."""
+        from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
+
+        stack = DeviceMemStack.instance()
         stack.malloc(piece), stack.malloc(piece)
         stack.free(piece), stack.free(piece)
 
-    def unpad_reconstructed_data_estimator(self, fde, n, raw_nz, odd_horiz, recon_size):
-        """STEP 4 (reference twin :968-989): the reconstruction is allocated, the grid released; like the reference,
-        the result itself is not kept on the stack."""
+    def unpad_reconstructed_data_estimator(self, n, raw_nz, odd_horiz, recon_size):
+        """STEP 4 (reference twin :968-989): the reconstruction, allocated before the chunk loop.  Returns its shape and
+        bytes (the caller releases it: like the reference, the result itself is not kept on the stack)."""
         from tomobar_b200.supp.memory_estimator_helpers import DeviceMemStack
 
-        stack = DeviceMemStack.instance()
         odd_recon = bool(recon_size % 2)
         um = (n - odd_horiz) // 2 - recon_size // 2
         up = (n - odd_horiz) // 2 + (recon_size + odd_recon) // 2
         recon_shape = (raw_nz, up - um, up - um)
         recon = int(np.prod(recon_shape)) * 4
-        stack.malloc(recon)
-        stack.free(fde)
-        stack.free(recon)
-        return recon_shape
+        DeviceMemStack.instance().malloc(recon)
+        return recon_shape, recon
 
     def _fourier_filter(self, data, raw_width, width, power_of_2_oversampling, oversampling_level, filter_type,
                         cutoff_freq, pack_into=None):
@@ -408,23 +425,52 @@ class RecToolsDIRCuPy:
         wfilter = torch.as_tensor(calc_filter(over, filter_type, cutoff_freq), device=dev)
         t = torch.fft.rfftfreq(over, device=dev).to(torch.float32)
         w = wfilter * torch.exp((-2 * np.pi * 1j * rotation_axis) * t.to(torch.complex64))
+        if over % 2 == 0:
+            # irfft is defined to ignore the imaginary part of the Nyquist bin, which the phase ramp makes non-zero
+            # (purely imaginary for a centred axis); cuFFT's c2r result is undefined for such input and measurably
+            # uses it at 8192-point rows (7.7e-3 relative against a float64 irfft at config 4) -- the bin is made real
+            torch.view_as_real(w)[over // 2, 1] = 0.0
         nz, nproj, _ = data.shape
         # slice chunks bound the oversampled temporaries (the reference chunks for the same reason)
         per = max(1, (1 << 27) // (nproj * over))
         if pack_into is not None and per > 1:
             per -= per % 2  # whole slice pairs per chunk
         fused = pack_into is not None and per % 2 == 0 and nz % 2 == 0
-        out = None if fused else torch.empty((nz, nproj, width), dtype=torch.float32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
+        if fused and over % 2 == 0 and self._FILTER_SLICE_PAIRS:
+            # Slice PAIRS are filtered as complex rows: the filter's impulse response is real (the Nyquist bin of the
+            # two-sided spectrum is the real one above), hence real and imaginary part are filtered independently -- one c2c transform pair per slice pair instead of an r2c / c2r pair per
+            # slice, no c2r input clone, and the 1 / over of the inverse transform folded into the filter.
+            h = over // 2
+            wfull = torch.empty(over, dtype=torch.complex64, device=dev)
+            wfull[:h] = w[:h]
+            wfull[h] = w[h]
+            wfull[h + 1:] = torch.conj(w[1:h]).flip(0)
+            wfull *= 1.0 / over
+            data = data.contiguous()
+            for z0 in range(0, nz, per):
+                cnt = min(per, nz - z0) // 2
+                tmp = torch.empty((cnt, nproj, over), dtype=torch.complex64, device=dev)
+                check(lib.tmb_edge_pad_pair(ptr(data[z0:]), ptr(tmp), cnt, nproj, raw_width, over, padding_m, st),
+                      "tmb_edge_pad_pair")
+                tmp = torch.fft.fft(tmp, dim=2)
+                tmp.mul_(wfull)
+                tmp = torch.fft.ifft(tmp, dim=2, norm="forward")
+                check(lib.tmb_fi_crop_sign(ptr(tmp) + 8 * unpad_m, over, ptr(pack_into[z0 // 2:]), width, cnt * nproj, st),
+                      "tmb_fi_crop_sign")
+            return None
+        out = None if fused else torch.empty((nz, nproj, width), dtype=torch.float32, device=dev)
         for z0 in range(0, nz, per):
             tmp = edge_pad(data[z0:z0 + per], padding_m, raw_width + 2 * padding_m)
             tmp = torch.fft.irfft(w * torch.fft.rfft(tmp, dim=2), n=over, dim=2)
-            if fused:
+            if fused:  # crop and pack straight out of the oversampled irfft output
                 check(lib.tmb_fi_pack_rows(ptr(tmp) + 4 * unpad_m, over, nproj * over, ptr(pack_into[z0 // 2:]), width, nproj,
                                            tmp.shape[0] // 2, st), "tmb_fi_pack_rows")
             else:
                 out[z0:z0 + per] = tmp[:, :, unpad_m:unpad_p]
-        if pack_into is not None and not fused:
+        if fused:
+            return None
+        if pack_into is not None:
             check(lib.tmb_fi_pack(ptr(out), ptr(pack_into), width, nproj, nz // 2, st), "tmb_fi_pack")
             return None
         return out

@@ -12,7 +12,10 @@ from tomobar_b200._tensors import ptr  # noqa: E402
 dev = torch.device("cuda", 0)
 st = torch.cuda.current_stream(dev).cuda_stream
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for n, na, nz, span in ((2048, 2000, 128, np.pi), (362, 241, 10, np.pi), (256, 180, 6, 2 * np.pi), (1024, 900, 64, np.pi)):
+SHAPES = ((2048, 2000, 128, np.pi), (362, 241, 10, np.pi), (256, 180, 6, 2 * np.pi), (1024, 900, 64, np.pi))
+if len(sys.argv) >= 4:  # python tools/check_gather.py n nangles nz
+    SHAPES = ((int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), np.pi),)
+for n, na, nz, span in SHAPES:
     nz2 = nz // 2
     angles = np.linspace(0, span, na, endpoint=False).astype(np.float32)
     theta = torch.as_tensor(-angles, dtype=torch.float32, device=dev)
