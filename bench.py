@@ -331,6 +331,9 @@ def main():
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tmb", choices=["tmb", "reference"])
+    ap.add_argument("--timeline", default=None, metavar="FILE",
+                    help="after the timed region, run one more step under torch.profiler and write the device timeline "
+                         "(busy / idle time, largest gaps, time per kernel) of this rank to FILE.rank<r> (iterative configs)")
     ap.add_argument("--config", default="headline", choices=sorted(CONFIGS),
                     help="BASELINE.json configuration: headline (default: FISTA-OS 24 + PD_TV at 2048^2 x 512 / 1800), "
                          "c1 (2-D FBP 256^2, the CPU methodsDIR case), c2 (FISTA-OS 6 + PD_TV, 1024^2 x 256 / 900), "
@@ -706,6 +709,18 @@ def run_iterative(args, cfg):
         ms_total = float(tt.item())
     ms_step = ms_total / args.steps
     value = 1000.0 / (ms_step * os_n)  # outer iterations per second for the whole (sharded) volume
+
+    if args.timeline:
+        # outside the timed region: one more sub-step under the profiler (device busy / idle time, gaps, kernels)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from timeline import device_timeline
+
+        barrier()
+        report = device_timeline(substep, f"{cfg.get('name', args.config)} sub-step, rank {rank} of {world} "
+                                          f"({ms_step:.2f} ms per step in the timed region)")
+        with open(f"{args.timeline}.rank{rank}", "w") as fh:
+            fh.write(report + "\n")
+        barrier()
 
     # ---- per-kernel timings (CUDA events on the launching stream) ------------------------------
     def timed(fn, reps):
