@@ -119,7 +119,9 @@ __device__ __forceinline__ int upper_bound_f(const float *__restrict__ a, int n,
 }
 
 // contribution of polar line `proj` to the grid point (fft_us_kernels.cu:379-466)
-template <int SC = FI_SC>
+// FULL: all SC slices of the chunk exist (no per-slice predicate: 46 instead of 70 instructions per sample at SC = 8 --
+// the predicated loads cost a compare and two register moves each)
+template <int SC = FI_SC, bool FULL = false>
 __device__ __forceinline__ void fi_line(const float2 *__restrict__ g, float theta, float2 (&acc)[SC], float px,
                                         float py, float radius_2, int proj, int z0, int nzc, float coeff0,
                                         float coeff1, int n, int nproj) {
@@ -160,7 +162,7 @@ __device__ __forceinline__ void fi_line(const float2 *__restrict__ g, float thet
     const float w = coeff0 * exp_ftz(coeff1 * (w0 * w0 + w1 * w1));
 #pragma unroll
     for (int s = 0; s < SC; ++s) {
-      if (s < nzc) {
+      if (FULL || s < nzc) {
         const float2 v = __ldg(row + (size_t)s * plane + ri);
         acc[s].x += v.x * w;
         acc[s].y += v.y * w;
@@ -428,7 +430,7 @@ constexpr int FW_PX = 8, FW_PY = 4;  // the patch of a warp
 #define FW_MINB 4  // CTAs per SM the register allocation aims at (5: 96 registers with spills, 56 instead of 50 ms at config 4)
 #endif
 
-template <int SC>
+template <int SC, bool FULL>
 __global__ void __launch_bounds__(128, FW_MINB)
     k_fi_gather_w(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta,
                   const float *__restrict__ sth, const int *__restrict__ sidx, int m, float mu, int n, int nproj,
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(128, FW_MINB)
         // the reference's own test to what is left
         const float dq = py * ct - px * st;
         if (dq * dq > radius_2 * 1.01f + 1e-12f) continue;
-        fi_line<SC>(g, th, acc, px, py, radius_2, proj, z0, nzc, coeff0, coeff1, n, nproj);
+        fi_line<SC, FULL>(g, th, acc, px, py, radius_2, proj, z0, nzc, coeff0, coeff1, n, nproj);
       }
     }
     // the (-1)^(x+y) of the centred inverse 2-D FFT (c2dfftshift, :588-609) is applied on the way out
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(128, FW_MINB)
     const size_t o = (size_t)ty * n2 + tx;
 #pragma unroll
     for (int s = 0; s < SC; ++s)
-      if (s < nzc) f[(size_t)(z0 + s) * fs2 + o] = make_float2(acc[s].x * sg, acc[s].y * sg);
+      if (FULL || s < nzc) f[(size_t)(z0 + s) * fs2 + o] = make_float2(acc[s].x * sg, acc[s].y * sg);
   }
 }
 
@@ -653,8 +655,11 @@ static int g_fi_gather_mode = 0;
 // test hook: complex slices per thread of k_fi_gather_w (2, 4, 8, 16; 0 = default)
 static int g_fi_sc = 0;
 constexpr int FW_SC_DEFAULT = 4;
+static bool g_fi_no_full = false;  // test hook: sc + 100 keeps the per-slice predicates on full chunks too (A/B timing)
 extern "C" int tmb_fi_set_slices_per_thread(int sc) {
-  const int old = g_fi_sc;
+  const int old = g_fi_sc + (g_fi_no_full ? 100 : 0);
+  g_fi_no_full = sc >= 100;
+  if (sc >= 100) sc -= 100;
   g_fi_sc = (sc == 2 || sc == 4 || sc == 8 || sc == 16) ? sc : 0;
   return old;
 }
@@ -675,14 +680,17 @@ static int fi_gather_launch(const float *datac, float *fde, const float *theta, 
     // 16 complex slices, as FOURIER_INV launches it: 4 -> 15.3, 8 -> 13.9, 16 -> 18.3 ms; at 5 slices 4 is best)
     const int sc = g_fi_sc ? g_fi_sc : (nz2 >= 16 ? 8 : FW_SC_DEFAULT);
     const dim3 wgrid((center_size + 31) / 32, (center_size + FW_PY - 1) / FW_PY, (nz2 + sc - 1) / sc);
-#define TMB_FW(SC_)                                                                                                  \
-  k_fi_gather_w<SC_><<<wgrid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),               \
-                                                              reinterpret_cast<float2 *>(fde), theta, sorted_theta, \
-                                                              sorted_idx, m, mu, n, nproj, nz2, center_size)
-    if (sc == 16) TMB_FW(16);
-    else if (sc == 8) TMB_FW(8);
-    else if (sc == 2) TMB_FW(2);
-    else TMB_FW(4);
+    const bool full = nz2 % sc == 0 && !g_fi_no_full;  // every z-block holds sc slices: the kernel without per-slice predicates
+#define TMB_FW(SC_, FULL_)                                                                                           \
+  k_fi_gather_w<SC_, FULL_><<<wgrid, 128, 0, (cudaStream_t)stream>>>(                                                \
+      reinterpret_cast<const float2 *>(datac), reinterpret_cast<float2 *>(fde), theta, sorted_theta, sorted_idx, m, mu, \
+      n, nproj, nz2, center_size)
+#define TMB_FW2(SC_) do { if (full) TMB_FW(SC_, true); else TMB_FW(SC_, false); } while (0)
+    if (sc == 16) TMB_FW2(16);
+    else if (sc == 8) TMB_FW2(8);
+    else if (sc == 2) TMB_FW2(2);
+    else TMB_FW2(4);
+#undef TMB_FW2
 #undef TMB_FW
     return check_launch("k_fi_gather_w");
   }

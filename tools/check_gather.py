@@ -26,9 +26,20 @@ for n, na, nz, span in SHAPES:
     m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(1e-4) + (mu * n) * (mu * n) / 4)))
     fde = torch.empty((nz2, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
     ref = None
-    for mode in (1, 2, 3, 38, 316, 0):  # 3x: k_fi_gather_w with x complex slices per thread
+    # mode 3x / 31x: k_fi_gather_w with x complex slices per thread; 4xx: the same with the per-slice predicates kept on
+    # full chunks (sc + 100 of the hook)
+    for mode in (1, 2, 3, 38, 316, 408, 416, 0):
         lib.tmb_fi_set_gather(3 if mode > 3 else mode)
-        lib.tmb_fi_set_slices_per_thread((mode - 300 if mode > 300 else mode - 30) if mode > 3 else (4 if mode == 3 else 0))
+        sc = 0
+        if mode == 3:
+            sc = 4
+        elif mode >= 400:
+            sc = 100 + mode - 400
+        elif mode > 300:
+            sc = mode - 300
+        elif mode > 3:
+            sc = mode - 30
+        lib.tmb_fi_set_slices_per_thread(sc)
         fn = lambda: check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
                                              float(np.float32(mu)), n, na, nz2, st), "g")
         fde.fill_(float("nan"))
