@@ -491,13 +491,16 @@ def run_direct(args, cfg):
         fde = torch.empty((chunk, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
         mu = -np.log(1e-4) / (2 * n * n)
         m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(1e-4) + (mu * n) * (mu * n) / 4)))
-        ms_k = _timed(torch, lambda: check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta),
-                                                             ptr(sorted_idx), m, float(np.float32(mu)), n, na, chunk, st),
+        # (the entry point FOURIER_INV calls for these sizes: polar samples stored as slice pairs when every chunk is
+        # whole blocks of 8 complex slices)
+        gather = lib.tmb_fi_gather_pairs if (nz2 % 8 == 0 and chunk % 8 == 0) else lib.tmb_fi_gather
+        ms_k = _timed(torch, lambda: check(gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta),
+                                                  ptr(sorted_idx), m, float(np.float32(mu)), n, na, chunk, st),
                                            "tmb_fi_gather"), 6)
         bytes_k = 8.0 * chunk * na * n + 8.0 * chunk * 4 * n * n  # polar samples read once, grid written once
         kname = (f"k_fi_gather_w (USFFT gather onto the 2n x 2n grid, {chunk} complex slices per launch, {n_chunks} launches "
-                 "per step; a warp walks the polar lines of its patch in lock step: issue-bound, the grid write is its "
-                 "algorithmic HBM traffic)")
+                 "per step; a warp walks the polar lines of its patch in lock step, samples read as slice pairs: "
+                 "issue-bound, the grid write is its algorithmic HBM traffic)")
         traffic = traffic_of("k_fi_gather_w", int(chunk) * 4 * n * n)
         del datac, fde
         # pad + crop per filter chunk, scale-sign, gather + unpad per grid chunk (+ torch's spectrum product and cuFFT's

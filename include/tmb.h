@@ -246,6 +246,12 @@ int tmb_fi_pack_rows(const float *in, size_t row_pitch, size_t slice_pitch, floa
 int tmb_edge_pad_pair(const float *in, float *out, int nzc, size_t rows, int w, int wout, int pad_left, void *stream);
 int tmb_fi_crop_sign(const float *in, size_t row_pitch, float *datac, int n, size_t rows, void *stream);
 int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz2, void *stream);
+/* tmb_fi_scale_sign out of place into the slice-PAIR layout dataz[nz2 / 2][nproj][n] of (slice 2t, slice 2t + 1) (nz2 even),
+ * and the whole-grid gather reading it (tmb_fi_gather with one 128-bit load per two slices; nz2 a multiple of 8):
+ * c1dfftshift :559-586 and gather_kernel_center :468-527 as above, same bits */
+int tmb_fi_scale_sign_pairs(const float *datac, float *dataz, float c, int n, int nproj, int nz2, void *stream);
+int tmb_fi_gather_pairs(const float *dataz, float *fde, const float *theta, const float *sorted_theta,
+                        const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream);
 /* test hook: 1 = k_fi_gather (every thread walks its own polar lines), 2 = k_fi_gather_s (samples of a tile staged in
  * shared memory), 3 = k_fi_gather_w (a warp walks the lines of its 8 x 4 patch in lock step), 0 = the measured best (3).
  * Returns the old value. */

@@ -203,3 +203,23 @@ def test_fourier_filter_8192_point_rows_vs_float64(pairs):
     ref = torch.complex(y[0::2] * sgn, y[1::2] * sgn)
     err = float((datac - ref).norm() / ref.norm())
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("nz,na,detX", [(16, 90, 128), (32, 64, 96), (48, 50, 64), (16, 120, 97)])
+def test_fourier_inv_slice_pair_gather_is_bit_identical(nz, na, detX):
+    """The whole-grid gather reading polar samples stored as slice pairs (tmb_fi_scale_sign_pairs -> tmb_fi_gather_pairs,
+    one 128-bit load per two slices, 8 or 16 complex slices per thread) against the planar layout: same visits in the same
+    order, the same reconstruction bit for bit (gather_kernel_center, fft_us_kernels.cu:468-527).  (Detector widths whose
+    transforms cuFFT runs with radix 5 -- 80, 160 -- are avoided: there two calls of the SAME path differ in the last bit.)"""
+    from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
+
+    g = torch.Generator(device="cuda").manual_seed(nz + na)
+    d = torch.rand((nz, na, detX), device="cuda", generator=g)
+    angles = np.linspace(0, math.pi, na, endpoint=False).astype(np.float32)
+    T = RecToolsDIRCuPy(detX, 0, nz, 0.0, angles, detX, device_projector=0)
+    out = []
+    for pairs in (True, False):
+        T._GATHER_SLICE_PAIRS = pairs
+        out.append(T.FOURIER_INV(d))
+    assert torch.isfinite(out[0]).all()
+    assert torch.equal(out[0], out[1])

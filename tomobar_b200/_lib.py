@@ -64,6 +64,8 @@ SIGNATURES = {
     "tmb_edge_pad_pair": (_i, [_fp, _fp, _i, _sz, _i, _i, _i, _vp]),
     "tmb_fi_crop_sign": (_i, [_fp, _sz, _fp, _i, _sz, _vp]),
     "tmb_fi_scale_sign": (_i, [_fp, _f, _i, _i, _i, _vp]),
+    "tmb_fi_scale_sign_pairs": (_i, [_fp, _fp, _f, _i, _i, _i, _vp]),
+    "tmb_fi_gather_pairs": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _vp]),
     "tmb_fi_set_gather": (_i, [_i]),
     "tmb_fi_set_slices_per_thread": (_i, [_i]),
     "tmb_fi_gather": (_i, [_fp, _fp, _fp, _fp, _vp, _i, _f, _i, _i, _i, _vp]),

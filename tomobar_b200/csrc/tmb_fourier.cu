@@ -79,6 +79,25 @@ __global__ void k_fi_scale_sign(float2 *__restrict__ d, float c, int n, size_t r
   }
 }
 
+// c1dfftshift (:559-586) out of place into the slice-PAIR layout of the gather: out[t][row][x] = (in[2t][row][x],
+// in[2t + 1][row][x]) * c * (-1)^(x+1).  Same traffic as the in-place pass; the products are rounded as there.
+__global__ void k_fi_scale_sign_pairs(const float2 *__restrict__ in, float4 *__restrict__ out, float c, int n,
+                                      size_t rows_per_slice, size_t rows) {
+  const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tx >= n) return;
+  const float sgn = (tx & 1) ? 1.f : -1.f;
+  for (size_t r = blockIdx.y; r < rows; r += gridDim.y) {  // r = t * rows_per_slice + row
+    const size_t t = r / rows_per_slice, row = r - t * rows_per_slice;
+    float2 a = in[((2 * t) * rows_per_slice + row) * n + tx], b = in[((2 * t + 1) * rows_per_slice + row) * n + tx];
+    if (c == 1.f) {
+      a.x = a.x * sgn; a.y = a.y * sgn; b.x = b.x * sgn; b.y = b.y * sgn;
+    } else {
+      a.x = a.x * c * sgn; a.y = a.y * c * sgn; b.x = b.x * c * sgn; b.y = b.y * c * sgn;
+    }
+    out[r * n + tx] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
 __global__ void k_fi_sign2d(float2 *__restrict__ f, int n2, int nz2) {
   const int tx = blockIdx.x * blockDim.x + threadIdx.x;
   const int ty = blockIdx.y * blockDim.y + threadIdx.y;
@@ -121,7 +140,9 @@ __device__ __forceinline__ int upper_bound_f(const float *__restrict__ a, int n,
 // contribution of polar line `proj` to the grid point (fft_us_kernels.cu:379-466)
 // FULL: all SC slices of the chunk exist (no per-slice predicate: 46 instead of 70 instructions per sample at SC = 8 --
 // the predicated loads cost a compare and two register moves each)
-template <int SC = FI_SC, bool FULL = false>
+// Z2: the polar samples are stored as slice PAIRS, g4[nz2 / 2][nproj][n] of (slice 2t, slice 2t + 1): one 128-bit load
+// and one address per two slices (needs FULL and an even z0)
+template <int SC = FI_SC, bool FULL = false, bool Z2 = false>
 __device__ __forceinline__ void fi_line(const float2 *__restrict__ g, float theta, float2 (&acc)[SC], float px,
                                         float py, float radius_2, int proj, int z0, int nzc, float coeff0,
                                         float coeff1, int n, int nproj) {
@@ -160,12 +181,24 @@ __device__ __forceinline__ void fi_line(const float2 *__restrict__ g, float thet
     y0 = fminf(y0, (float)(0.5f - 1e-5));
     const float w0 = px - x0, w1 = py - y0;
     const float w = coeff0 * exp_ftz(coeff1 * (w0 * w0 + w1 * w1));
+    if constexpr (Z2) {
+      const float4 *row4 = reinterpret_cast<const float4 *>(g) + (size_t)proj * n + (size_t)(z0 >> 1) * plane;
 #pragma unroll
-    for (int s = 0; s < SC; ++s) {
-      if (FULL || s < nzc) {
-        const float2 v = __ldg(row + (size_t)s * plane + ri);
-        acc[s].x += v.x * w;
-        acc[s].y += v.y * w;
+      for (int s = 0; s < SC / 2; ++s) {
+        const float4 v = __ldg(row4 + (size_t)s * plane + ri);
+        acc[2 * s].x += v.x * w;
+        acc[2 * s].y += v.y * w;
+        acc[2 * s + 1].x += v.z * w;
+        acc[2 * s + 1].y += v.w * w;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < SC; ++s) {
+        if (FULL || s < nzc) {
+          const float2 v = __ldg(row + (size_t)s * plane + ri);
+          acc[s].x += v.x * w;
+          acc[s].y += v.y * w;
+        }
       }
     }
   }
@@ -430,7 +463,7 @@ constexpr int FW_PX = 8, FW_PY = 4;  // the patch of a warp
 #define FW_MINB 4  // CTAs per SM the register allocation aims at (5: 96 registers with spills, 56 instead of 50 ms at config 4)
 #endif
 
-template <int SC, bool FULL>
+template <int SC, bool FULL, bool Z2 = false>
 __global__ void __launch_bounds__(128, FW_MINB)
     k_fi_gather_w(const float2 *__restrict__ g, float2 *__restrict__ f, const float *__restrict__ theta,
                   const float *__restrict__ sth, const int *__restrict__ sidx, int m, float mu, int n, int nproj,
@@ -519,7 +552,7 @@ __global__ void __launch_bounds__(128, FW_MINB)
         // the reference's own test to what is left
         const float dq = py * ct - px * st;
         if (dq * dq > radius_2 * 1.01f + 1e-12f) continue;
-        fi_line<SC, FULL>(g, th, acc, px, py, radius_2, proj, z0, nzc, coeff0, coeff1, n, nproj);
+        fi_line<SC, FULL, Z2>(g, th, acc, px, py, radius_2, proj, z0, nzc, coeff0, coeff1, n, nproj);
       }
     }
     // the (-1)^(x+y) of the centred inverse 2-D FFT (c2dfftshift, :588-609) is applied on the way out
@@ -649,6 +682,17 @@ extern "C" int tmb_fi_scale_sign(float *datac, float c, int n, int nproj, int nz
   return check_launch("k_fi_scale_sign");
 }
 
+extern "C" int tmb_fi_scale_sign_pairs(const float *datac, float *dataz, float c, int n, int nproj, int nz2, void *stream) {
+  TMB_REQUIRE(datac && dataz && datac != dataz && n > 0 && nproj > 0 && nz2 > 0 && nz2 % 2 == 0 &&
+                  reinterpret_cast<uintptr_t>(dataz) % 16 == 0,
+              "tmb_fi_scale_sign_pairs: bad argument");
+  const size_t rows = (size_t)nproj * (nz2 / 2);
+  dim3 grid((n + 127) / 128, (unsigned)(rows < 4096 ? rows : 4096));
+  k_fi_scale_sign_pairs<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(datac),
+                                                                reinterpret_cast<float4 *>(dataz), c, n, (size_t)nproj, rows);
+  return check_launch("k_fi_scale_sign_pairs");
+}
+
 // test hook: 1 = k_fi_gather (every thread walks its own lines), 2 = k_fi_gather_s (a tile's samples staged in shared
 // memory), 3 = k_fi_gather_w (a warp walks its patch's lines in lock step); 0 = the measured best (3)
 static int g_fi_gather_mode = 0;
@@ -675,10 +719,10 @@ static int fi_gather_launch(const float *datac, float *fde, const float *theta, 
   dim3 block(32, 4), grid((center_size + 31) / 32, (center_size + 3) / 4, (nz2 + FI_SC - 1) / FI_SC);
   if (g_fi_gather_mode == 3 || g_fi_gather_mode == 0) {
     // complex slices per thread: g_fi_sc (test hook) or the measured best
-    // (measured at 2048^2, 2000 angles, 64 complex slices: 4 -> 60.9, 8 -> 55.6, 16 -> 50.7 ... 64.8 ms depending on the
-    // box (the 128-register build of 16 is the only variant whose time moves between boxes), 32 -> 232 ms (spills);
-    // 16 complex slices, as FOURIER_INV launches it: 4 -> 15.3, 8 -> 13.9, 16 -> 18.3 ms; at 5 slices 4 is best)
-    const int sc = g_fi_sc ? g_fi_sc : (nz2 >= 16 ? 8 : FW_SC_DEFAULT);
+    // (measured at 2048^2, 2000 angles, 16 complex slices per launch as FOURIER_INV launches it, with the per-slice
+    // predicates: 4 -> 15.3, 8 -> 13.9, 16 -> 18.3 ... 22 ms (the predicated 128-register build of 16 is the one variant
+    // whose time moves between boxes); FULL: 8 -> 11.5, 16 -> 10.2 ms; 32 per thread spill; at 5 slices 4 is best)
+    const int sc = g_fi_sc ? g_fi_sc : (nz2 % 16 == 0 ? 16 : (nz2 >= 16 ? 8 : FW_SC_DEFAULT));
     const dim3 wgrid((center_size + 31) / 32, (center_size + FW_PY - 1) / FW_PY, (nz2 + sc - 1) / sc);
     const bool full = nz2 % sc == 0 && !g_fi_no_full;  // every z-block holds sc slices: the kernel without per-slice predicates
 #define TMB_FW(SC_, FULL_)                                                                                           \
@@ -712,6 +756,27 @@ extern "C" int tmb_fi_gather(const float *datac, float *fde, const float *theta,
   TMB_REQUIRE(datac && fde && theta && sorted_theta && sorted_idx, "tmb_fi_gather: null argument");
   TMB_REQUIRE(n > 0 && nproj > 0 && nz2 > 0 && m > 0 && mu > 0.f, "tmb_fi_gather: bad argument");
   return fi_gather_launch(datac, fde, theta, sorted_theta, sorted_idx, m, mu, n, nproj, nz2, 2 * n, stream);
+}
+
+// the whole-grid gather from polar samples in the slice-pair layout of tmb_fi_scale_sign_pairs (one 128-bit load per two
+// slices: 16 -> 8 loads and addresses per sample at 16 slices per thread); nz2 must be a multiple of 8
+extern "C" int tmb_fi_gather_pairs(const float *dataz, float *fde, const float *theta, const float *sorted_theta,
+                                   const int *sorted_idx, int m, float mu, int n, int nproj, int nz2, void *stream) {
+  TMB_REQUIRE(dataz && fde && theta && sorted_theta && sorted_idx && m >= 0 && n > 0 && nproj > 0 && nz2 > 0 &&
+                  nz2 % 8 == 0 && reinterpret_cast<uintptr_t>(dataz) % 16 == 0,
+              "tmb_fi_gather_pairs: bad argument");
+  const int center_size = 2 * n;
+  const int sc = (g_fi_sc == 8 || nz2 % 16 != 0) ? 8 : 16;
+  const dim3 wgrid((center_size + 31) / 32, (center_size + FW_PY - 1) / FW_PY, nz2 / sc);
+  if (sc == 16)
+    k_fi_gather_w<16, true, true><<<wgrid, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(dataz), reinterpret_cast<float2 *>(fde), theta, sorted_theta, sorted_idx, m, mu, n,
+        nproj, nz2, center_size);
+  else
+    k_fi_gather_w<8, true, true><<<wgrid, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2 *>(dataz), reinterpret_cast<float2 *>(fde), theta, sorted_theta, sorted_idx, m, mu, n,
+        nproj, nz2, center_size);
+  return check_launch("k_fi_gather_w (slice pairs)");
 }
 
 extern "C" int tmb_fi_gather_center(const float *datac, float *fde, const float *theta, const float *sorted_theta,

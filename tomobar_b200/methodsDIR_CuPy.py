@@ -111,6 +111,7 @@ class RecToolsDIRCuPy:
     # ------------------------------------------------------------------------------------------
     _FILTERS = ("none", "ramp", "shepp", "cosine", "cosine2", "hamming", "hann", "parzen")
     _CENTER_SIZE_MIN = 192  # methodsDIR_CuPy.py:23
+    _GATHER_SLICE_PAIRS = True  # FOURIER_INV's whole-grid gather reads polar samples stored as slice pairs (False: planar)
     _FILTER_SLICE_PAIRS = True  # FOURIER_INV filters slice pairs as complex rows (False: an r2c / c2r pair per slice)
 
     def FOURIER_INV(self, data, **kwargs) -> torch.Tensor:
@@ -212,16 +213,27 @@ class RecToolsDIRCuPy:
             del data
             # STEP 1b: 1-D FFT along the detector (:725-754)
             datac = torch.fft.fft(datac, dim=-1)
-            check(lib.tmb_fi_scale_sign(ptr(datac), float(np.float32(4 / n)), n, nproj, nz2, st), "tmb_fi_scale_sign")
+            center_size = min(center_size, 2 * n)
+            center_size -= center_size % 2
+            whole = center_size >= self._CENTER_SIZE_MIN and center_size == 2 * n
+            partial = center_size >= self._CENTER_SIZE_MIN
+            chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))  # complex slices per pass of STEPS 2-4
+            # the whole-grid gather reads slice PAIRS (one 128-bit load per two slices) when every chunk is whole
+            # blocks of 8 complex slices: the scale / sign pass writes that layout instead of working in place
+            pairs = whole and self._GATHER_SLICE_PAIRS and nz2 % 8 == 0 and chunk % 8 == 0
+            if pairs:
+                dataz = torch.empty_like(datac)
+                check(lib.tmb_fi_scale_sign_pairs(ptr(datac), ptr(dataz), float(np.float32(4 / n)), n, nproj, nz2, st),
+                      "tmb_fi_scale_sign_pairs")
+                datac = dataz
+                del dataz
+            else:
+                check(lib.tmb_fi_scale_sign(ptr(datac), float(np.float32(4 / n)), n, nproj, nz2, st), "tmb_fi_scale_sign")
             m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(eps) + (mu * n) * (mu * n) / 4)))
             # STEP 2: polar samples onto the 2n x 2n Cartesian grid (:756-835); the (-1)^(x+y) before the 2-D
             # FFT is applied by these kernels, the one after it by the unpadding kernel.  Three branches, chosen
             # by the centre size like the reference: the whole grid gathered (default), a centre square gathered
             # and the rest scattered with atomic adds, or everything scattered (centre below _CENTER_SIZE_MIN)
-            center_size = min(center_size, 2 * n)
-            center_size -= center_size % 2
-            whole = center_size >= self._CENTER_SIZE_MIN and center_size == 2 * n
-            partial = center_size >= self._CENTER_SIZE_MIN
             # STEP 4's geometry: crop, de-apodise, unpack the slice pairs (:920-966)
             odd_recon = bool(recon_size % 2)
             unpad_z = nz - odd_vert
@@ -232,15 +244,15 @@ class RecToolsDIRCuPy:
             # STEPS 2-4 run chunk by chunk of complex slices (the slices are independent): the oversampled grid only
             # ever exists for one chunk, the inverse 2-D FFT's output is read directly by the unpadding kernel (no
             # copy back into a whole-volume grid) and its 1 / (2n)^2 is applied there (no normalisation pass)
-            chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))
             mu32, inv_grid = float(np.float32(mu)), float(np.float32(1.0 / (4.0 * n * n)))
             for s0 in range(0, nz2, chunk):
                 c = min(chunk, nz2 - s0)
                 dc = ptr(datac[s0:])
                 if whole:
                     fde = torch.empty((c, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
-                    check(lib.tmb_fi_gather(dc, ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m, mu32, n,
-                                            nproj, c, st), "tmb_fi_gather")
+                    gather = lib.tmb_fi_gather_pairs if pairs else lib.tmb_fi_gather
+                    check(gather(dc, ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m, mu32, n, nproj, c, st),
+                          "tmb_fi_gather")
                 else:
                     # (the reference adds onto cp.empty memory in the partial branch, :661-670; zeros are what it means)
                     fde = torch.zeros((c, 2 * n, 2 * n), dtype=torch.complex64, device=dev)
@@ -372,6 +384,9 @@ class RecToolsDIRCuPy:
         stack.malloc(datac), stack.malloc(datac)      # FFT output + work area
         stack.free(datac), stack.free(datac)
         chunk = max(1, min(nz2, (1 << 28) // (4 * n * n)))
+        if self._GATHER_SLICE_PAIRS and nz2 % 8 == 0 and chunk % 8 == 0:
+            stack.malloc(datac)                       # the scale / sign pass writes the slice-pair layout out of place
+            stack.free(datac)                         # (whole-grid branch, the default centre size)
         return datac, chunk * (2 * n) * (2 * n) * 8
 
     def _fft_and_interpolation_estimator(self, piece):

@@ -56,6 +56,30 @@ for n, na, nz, span in SHAPES:
               f"{(d.norm() / ref.norm()).item():.2e}  max {d.abs().max().item():.2e} (|ref| max {ref.abs().max().item():.2e}) "
               f"finite={bool(torch.isfinite(r).all())}", flush=True)
     lib.tmb_fi_set_gather(0)
+    if nz2 % 8 == 0:  # the slice-pair layout (tmb_fi_scale_sign_pairs -> tmb_fi_gather_pairs), 8 and 16 slices per thread
+        dataz = torch.empty_like(datac)
+        check(lib.tmb_fi_scale_sign_pairs(ptr(datac), ptr(dataz), 1.0, n, na, nz2, st), "pairs")
+        check(lib.tmb_fi_scale_sign(ptr(datac), 1.0, n, na, nz2, st), "planar")
+        lib.tmb_fi_set_gather(1)
+        check(lib.tmb_fi_gather(ptr(datac), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m,
+                                float(np.float32(mu)), n, na, nz2, st), "g")
+        ref = torch.view_as_real(fde).clone()
+        lib.tmb_fi_set_gather(0)
+        for sc in (8, 16):
+            lib.tmb_fi_set_slices_per_thread(sc)
+            fn = lambda: check(lib.tmb_fi_gather_pairs(ptr(dataz), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx),
+                                                       m, float(np.float32(mu)), n, na, nz2, st), "gp")
+            fde.fill_(float("nan"))
+            fn(); torch.cuda.synchronize()
+            a.record()
+            for _ in range(3):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            d = torch.view_as_real(fde) - ref
+            print(f"n={n} na={na} nz={nz} m={m} mode pairs{sc}: {a.elapsed_time(b) / 3:8.2f} ms  rel-L2 vs mode 1 "
+                  f"{(d.norm() / ref.norm()).item():.2e}  max {d.abs().max().item():.2e} (|ref| max {ref.abs().max().item():.2e}) "
+                  f"finite={bool(torch.isfinite(fde.real).all())}", flush=True)
+        del dataz
     lib.tmb_fi_set_slices_per_thread(0)
     del datac, fde, ref, r, d
     torch.cuda.empty_cache()
