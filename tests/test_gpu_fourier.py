@@ -205,12 +205,55 @@ def test_fourier_filter_8192_point_rows_vs_float64(pairs):
     assert err < 2e-6, err
 
 
+@pytest.mark.parametrize("n,na,nz2", [(128, 90, 8), (96, 64, 16), (64, 50, 24), (80, 50, 40), (200, 97, 32)])
+def test_slice_pair_gather_is_bit_identical(n, na, nz2):
+    """tmb_fi_scale_sign_pairs -> tmb_fi_gather_pairs (polar samples stored as slice pairs, one 128-bit load per two slices,
+    8 or 16 complex slices per thread, no per-slice predicates) against tmb_fi_scale_sign -> k_fi_gather (hook 1: planar
+    samples, every thread walks its own lines, predicated scalar loads): same (point, line, sample) visits in the same
+    order, the same grid bit for bit -- as are the whole-chunk (FULL) planar variants at 4 / 8 / 16 slices per thread
+    (gather_kernel_center, fft_us_kernels.cu:468-527; c1dfftshift :559-586)."""
+    from tomobar_b200._lib import lib, check
+    from tomobar_b200._tensors import ptr
+
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    theta = torch.as_tensor(-np.linspace(0, math.pi, na, endpoint=False), dtype=torch.float32, device=dev)
+    sorted_theta, sorted_idx = torch.sort(theta)
+    sorted_idx = sorted_idx.to(torch.int32)
+    g = torch.Generator(device="cuda").manual_seed(n + nz2)
+    datac = torch.view_as_complex(torch.randn((nz2, na, n, 2), device=dev, generator=g))
+    dataz = torch.empty_like(datac)
+    c = float(np.float32(4 / n))
+    check(lib.tmb_fi_scale_sign_pairs(ptr(datac), ptr(dataz), c, n, na, nz2, st), "tmb_fi_scale_sign_pairs")
+    check(lib.tmb_fi_scale_sign(ptr(datac), c, n, na, nz2, st), "tmb_fi_scale_sign")
+    z = torch.view_as_real(dataz).view(nz2 // 2, na, n, 2, 2)
+    assert torch.equal(z[:, :, :, 0], torch.view_as_real(datac[0::2])) and torch.equal(z[:, :, :, 1], torch.view_as_real(datac[1::2]))
+    mu = -np.log(1e-4) / (2 * n * n)
+    m = int(np.ceil(2 * n * 1 / np.pi * np.sqrt(-mu * np.log(1e-4) + (mu * n) * (mu * n) / 4)))
+
+    def gather(fn, src, mode=0, sc=0):
+        fde = torch.full((nz2, 2 * n, 2 * n), float("nan"), dtype=torch.complex64, device=dev)
+        old_m, old_s = lib.tmb_fi_set_gather(mode), lib.tmb_fi_set_slices_per_thread(sc)
+        try:
+            check(fn(ptr(src), ptr(fde), ptr(theta), ptr(sorted_theta), ptr(sorted_idx), m, float(np.float32(mu)), n, na,
+                     nz2, st), "gather")
+        finally:
+            lib.tmb_fi_set_gather(old_m), lib.tmb_fi_set_slices_per_thread(old_s)
+        return torch.view_as_real(fde)
+
+    ref = gather(lib.tmb_fi_gather, datac, mode=1)
+    assert torch.isfinite(ref).all() and ref.abs().max() > 0
+    for sc in (0, 8, 16):
+        assert torch.equal(ref, gather(lib.tmb_fi_gather_pairs, dataz, sc=sc)), sc
+    for sc in (0, 4, 8, 16, 108):
+        assert torch.equal(ref, gather(lib.tmb_fi_gather, datac, mode=3, sc=sc)), sc
+
+
 @pytest.mark.parametrize("nz,na,detX", [(16, 90, 128), (32, 64, 96), (48, 50, 64), (16, 120, 97)])
-def test_fourier_inv_slice_pair_gather_is_bit_identical(nz, na, detX):
-    """The whole-grid gather reading polar samples stored as slice pairs (tmb_fi_scale_sign_pairs -> tmb_fi_gather_pairs,
-    one 128-bit load per two slices, 8 or 16 complex slices per thread) against the planar layout: same visits in the same
-    order, the same reconstruction bit for bit (gather_kernel_center, fft_us_kernels.cu:468-527).  (Detector widths whose
-    transforms cuFFT runs with radix 5 -- 80, 160 -- are avoided: there two calls of the SAME path differ in the last bit.)"""
+def test_fourier_inv_slice_pair_gather_matches_planar(nz, na, detX):
+    """FOURIER_INV through the slice-pair layout against the planar one.  The gathers are bit-identical (test above); the
+    whole call is compared to the last bit or two because cuFFT itself is not run-to-run reproducible at some batch counts
+    (24 or 40 complex slices: two calls of the SAME path differ by one ulp in every slice, tools/diag_pairs.py)."""
     from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
 
     g = torch.Generator(device="cuda").manual_seed(nz + na)
@@ -222,4 +265,4 @@ def test_fourier_inv_slice_pair_gather_is_bit_identical(nz, na, detX):
         T._GATHER_SLICE_PAIRS = pairs
         out.append(T.FOURIER_INV(d))
     assert torch.isfinite(out[0]).all()
-    assert torch.equal(out[0], out[1])
+    assert float((out[0] - out[1]).abs().max()) <= 1e-6 * float(out[1].abs().max())
