@@ -249,11 +249,11 @@ def test_slice_pair_gather_is_bit_identical(n, na, nz2):
         assert torch.equal(ref, gather(lib.tmb_fi_gather, datac, mode=3, sc=sc)), sc
 
 
-@pytest.mark.parametrize("nz,na,detX", [(16, 90, 128), (32, 64, 96), (48, 50, 64), (16, 120, 97)])
+@pytest.mark.parametrize("nz,na,detX", [(16, 90, 128), (32, 64, 96), (48, 50, 96), (80, 50, 100), (16, 120, 97)])
 def test_fourier_inv_slice_pair_gather_matches_planar(nz, na, detX):
-    """FOURIER_INV through the slice-pair layout against the planar one.  The gathers are bit-identical (test above); the
-    whole call is compared to the last bit or two because cuFFT itself is not run-to-run reproducible at some batch counts
-    (24 or 40 complex slices: two calls of the SAME path differ by one ulp in every slice, tools/diag_pairs.py)."""
+    """FOURIER_INV through the slice-pair layout against the planar one: bit-identical reconstructions.  (Detectors of
+    96 pixels and more: below a 192-point grid the method scatters with atomic adds like the reference, methodsDIR_CuPy.py
+    :761-779, the slice-pair gather is not involved and two calls differ in the last bit.)"""
     from tomobar_b200.methodsDIR_CuPy import RecToolsDIRCuPy
 
     g = torch.Generator(device="cuda").manual_seed(nz + na)
@@ -265,4 +265,4 @@ def test_fourier_inv_slice_pair_gather_matches_planar(nz, na, detX):
         T._GATHER_SLICE_PAIRS = pairs
         out.append(T.FOURIER_INV(d))
     assert torch.isfinite(out[0]).all()
-    assert float((out[0] - out[1]).abs().max()) <= 1e-6 * float(out[1].abs().max())
+    assert torch.equal(out[0], out[1])
