@@ -499,8 +499,8 @@ def run_direct(args, cfg):
                                            "tmb_fi_gather"), 6)
         bytes_k = 8.0 * chunk * na * n + 8.0 * chunk * 4 * n * n  # polar samples read once, grid written once
         kname = (f"k_fi_gather_w (USFFT gather onto the 2n x 2n grid, {chunk} complex slices per launch, {n_chunks} launches "
-                 "per step; a warp walks the polar lines of its patch in lock step, samples read as slice pairs: "
-                 "issue-bound, the grid write is its algorithmic HBM traffic)")
+                 "per step; a warp walks the polar lines of its patch in lock step, samples read as slice pairs: bound by the "
+                 "L1 data pipe (ncu: LSU wavefronts 72 % of peak), the grid write is its algorithmic HBM traffic)")
         traffic = traffic_of("k_fi_gather_w", int(chunk) * 4 * n * n)
         del datac, fde
         # pad + crop per filter chunk, scale-sign, gather + unpad per grid chunk (+ torch's spectrum product and cuFFT's
